@@ -1,0 +1,168 @@
+/*
+ * tdl.h -- C ABI of libtdl.so: the fused multi-scale view-synthesis loss of
+ * TripleDNet / FeatDepth / monodepth2, hand-written CUDA for sm_100a (B200).
+ *
+ * The reference (pure Python, no FFI of its own -- SURVEY.md section 8b) exposes this
+ * path only as methods of its net classes.  Each entry point below names the
+ * reference call sites it replaces (paths relative to the reference repository):
+ *
+ *   tdl_photo_fwd / tdl_photo_bwd
+ *       generate_images_pred            mono/model/mono_fm/net.py:157-170
+ *                                       mono/model/mono_baseline/net.py:123-135
+ *                                       mono/model/mono_fm_joint/net.py:181-194
+ *         = F.interpolate + disp_to_depth (net.py:135-140) + Backproject.forward
+ *           (mono/model/mono_fm/layers.py:57-61) + Project.forward (layers.py:73-82)
+ *           + F.grid_sample(border)
+ *       compute_reprojection_loss       mono/model/mono_fm/net.py:63-67  (SSIM layers.py:97-107,
+ *                                       robust_l1 net.py:55-57)
+ *       automask + min over frames      mono/model/mono_fm/net.py:90-106
+ *       disp mean-normalisation         mono/model/mono_fm/net.py:123-125
+ *       get_smooth_loss / gradient      mono/model/mono_fm/net.py:255-283
+ *       ... and the autograd backward of all of the above.
+ *   tdl_feat_fwd / tdl_feat_bwd
+ *       generate_features_pred          mono/model/mono_fm/net.py:172-199
+ *                                       mono/model/mono_fm_joint/net.py:196-223
+ *       compute_perceptional_loss + min mono/model/mono_fm/net.py:59-61,111-118
+ *                                       mono/model/mono_fm_joint_inpaint/net.py:58-70
+ *   tdl_edge_smooth_fwd / tdl_edge_smooth_bwd
+ *       get_feature_regularization_loss mono/model/mono_fm_joint/net.py:309-330
+ *
+ * Conventions
+ *   - every tensor is fp32, NCHW, contiguous, resident in device memory; only
+ *     min_index is int64 (the reference's torch.min index dtype).
+ *   - calls are asynchronous on `stream`, never allocate, never synchronise the host and
+ *     keep no state between calls: scratch lives in the caller-provided workspace, whose
+ *     contents must be preserved from a *_fwd call to the matching *_bwd call.
+ *   - return value: 0 = TDL_OK, < 0 = argument error (nothing was launched),
+ *     > 0 = a cudaError_t raised by a launch.  tdl_strerror() explains either.
+ *   - there is NO CPU implementation behind these symbols.
+ */
+#ifndef TDL_H_
+#define TDL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDL_ABI_VERSION 1
+#define TDL_MAX_SRC 4      /* source frames per target (frame_ids[1:])       */
+#define TDL_MAX_SCALES 4   /* disparity scales (opt.scales)                  */
+
+#define TDL_OK 0
+#define TDL_ERR_NULL (-1)      /* a required pointer is NULL                  */
+#define TDL_ERR_SHAPE (-2)     /* unsupported sizes (see each struct)         */
+#define TDL_ERR_WORKSPACE (-3) /* workspace_bytes smaller than *_ws_bytes()   */
+#define TDL_ERR_COUNT (-4)     /* S / nscales / C out of range                */
+#define TDL_ERR_NODEVICE (-5)  /* no CUDA device / not sm_100                 */
+
+typedef void* tdl_stream_t;    /* a cudaStream_t */
+
+/* ------------------------------------------------------------------ photometric + smoothness */
+typedef struct tdl_photo_args {
+    int32_t B, H, W;            /* batch, full-resolution height / width       */
+    int32_t S;                  /* number of source frames, 1..TDL_MAX_SRC      */
+    int32_t nscales;            /* 1..TDL_MAX_SCALES                            */
+    int32_t disp_h[TDL_MAX_SCALES], disp_w[TDL_MAX_SCALES];
+                                /* disp[s] is (B,1,disp_h[s],disp_w[s]); H/disp_h == W/disp_w
+                                   must be a power of two in {1,2,4,8,16,32}            */
+    int32_t automask;           /* != 0: identity channels precede the warped ones (net.py:90-95) */
+    int32_t disp_norm;          /* != 0: disp / (mean_hw(disp) + 1e-7) before smoothness           */
+    int32_t align_corners;      /* F.grid_sample convention; 0 = torch >= 1.3 default              */
+    int32_t reserved0;
+    double min_depth, max_depth;
+    float photo_coef[TDL_MAX_SCALES];   /* losses[s]          = photo_coef[s]  * mean_{b,y,x} min_c rho_c      */
+    float smooth_coef[TDL_MAX_SCALES];  /* losses[nscales+s]  = smooth_coef[s] * (sum of the six means)       */
+    float smooth_alpha;                 /* exp(-alpha * mean_c |d img|); the reference uses 0.5              */
+    float reserved1;
+    uint64_t noise_seed;        /* Philox seed used when automask and noise[s][f] == NULL               */
+
+    const float* target;                     /* (B,3,H,W)  inputs[("color",0,0)]                       */
+    const float* src[TDL_MAX_SRC];           /* (B,3,H,W)  inputs[("color",f,0)]                       */
+    const float* disp[TDL_MAX_SCALES];       /* outputs[("disp",0,s)]                                  */
+    const float* P;                          /* (B,S,3,4)  (K @ T_f)[:, :3, :]   (layers.py:74)        */
+    const float* invK;                       /* (B,3,3)    inv_K[:, :3, :3]      (layers.py:58)        */
+    const float* noise[TDL_MAX_SCALES][TDL_MAX_SRC];
+                                             /* (B,1,H,W) N(0,1) draws, scaled by 1e-5 in-kernel; NULL => Philox */
+    float* warped[TDL_MAX_SCALES][TDL_MAX_SRC];  /* out, optional: outputs[("color",f,s)] (B,3,H,W)      */
+    int64_t* min_index[TDL_MAX_SCALES];          /* out, optional: outputs[("min_index",s)] (B,H,W)      */
+    void* workspace;
+    uint64_t workspace_bytes;
+    float* losses;              /* out [2*nscales]: photometric per scale, then smoothness per scale    */
+
+    /* backward only */
+    const float* dlosses;       /* [2*nscales] upstream gradient of `losses` (device memory)           */
+    float* d_disp[TDL_MAX_SCALES];  /* out (B,1,disp_h[s],disp_w[s]), overwritten                       */
+    float* dP;                  /* out (B,S,3,4), overwritten                                          */
+} tdl_photo_args;
+
+/* ------------------------------------------------------------------ feature-metric */
+typedef struct tdl_feat_args {
+    int32_t B, C, h, w;         /* feature maps are (B,C,h,w); the reference uses h=H/2, w=W/2, C=64    */
+    int32_t S;
+    int32_t disp_h, disp_w;     /* disp is (B,1,disp_h,disp_w), resized bilinearly to (h,w)            */
+    int32_t align_corners;
+    double min_depth, max_depth;
+    float coef;                 /* loss = coef * mean_{b,y,x} min_f mean_c robust_l1                    */
+    float reserved0;
+
+    const float* tgt;                        /* (B,C,h,w)  extractor(color_0)[0]                       */
+    const float* src[TDL_MAX_SRC];           /* (B,C,h,w)  extractor(color_f)[0]                       */
+    const float* disp;
+    const float* P;                          /* (B,S,3,4) built from the half-resolution K            */
+    const float* invK;                       /* (B,3,3)   pinv(K_half)[:, :3, :3]                      */
+    float* warped[TDL_MAX_SRC];              /* out, optional: outputs[("feature",f,0)]               */
+    int64_t* min_index;                      /* out, optional (B,h,w)                                  */
+    void* workspace;
+    uint64_t workspace_bytes;
+    float* loss;                /* out [1]                                                              */
+
+    /* backward only */
+    const float* dloss;         /* [1] */
+    float* d_tgt;               /* out, optional (B,C,h,w), overwritten                                 */
+    float* d_src[TDL_MAX_SRC];  /* out, optional (all or none), overwritten (zero where not selected)   */
+    float* d_disp;              /* out (B,1,disp_h,disp_w), overwritten                                 */
+    float* dP;                  /* out (B,S,3,4), overwritten                                           */
+} tdl_feat_args;
+
+/* ------------------------------------------------------------------ edge-aware smoothness on C-channel maps */
+typedef struct tdl_edge_args {
+    int32_t B, C, h, w;         /* feature (B,C,h,w)                                                    */
+    int32_t H, W;               /* image (B,3,H,W); H/h == W/w must be a power of two <= 32             */
+    float alpha;                /* exp(-alpha * mean_c |d img|): 1.0 in get_feature_regularization_loss */
+    float first_coef;           /* loss = first_coef * (dx+dy terms) + second_coef * (dxx+dxy+dyx+dyy)  */
+    float second_coef;          /*        (the reference: -dis/2^i/5 and cvt/2^i/5)                     */
+    float reserved0;
+    const float* feature;
+    const float* image;
+    void* workspace;
+    uint64_t workspace_bytes;
+    float* loss;                /* out [1] */
+    const float* dloss;         /* [1], backward only */
+    float* d_feature;           /* out (B,C,h,w), overwritten, backward only */
+} tdl_edge_args;
+
+int tdl_abi_version(void);
+const char* tdl_strerror(int code);
+/* number of CUDA kernels (not memsets) one call launches -- used by bench.py's gpu_launches */
+int tdl_launch_count(const char* entry_point);
+
+uint64_t tdl_photo_ws_bytes(int32_t B, int32_t H, int32_t W, int32_t S, int32_t nscales,
+                            const int32_t* disp_h, const int32_t* disp_w);
+int tdl_photo_fwd(const tdl_photo_args* args, tdl_stream_t stream);
+int tdl_photo_bwd(const tdl_photo_args* args, tdl_stream_t stream);
+
+uint64_t tdl_feat_ws_bytes(int32_t B, int32_t C, int32_t h, int32_t w, int32_t S);
+int tdl_feat_fwd(const tdl_feat_args* args, tdl_stream_t stream);
+int tdl_feat_bwd(const tdl_feat_args* args, tdl_stream_t stream);
+
+uint64_t tdl_edge_ws_bytes(int32_t B, int32_t C, int32_t h, int32_t w);
+int tdl_edge_smooth_fwd(const tdl_edge_args* args, tdl_stream_t stream);
+int tdl_edge_smooth_bwd(const tdl_edge_args* args, tdl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDL_H_ */

@@ -213,7 +213,17 @@ def features_pred(spec: LossSpec, inputs, outputs, src_feats, inv_K_half=None):
     return outputs
 
 
-def photometric_scale(spec: LossSpec, inputs, outputs, scale, noise):
+def _select_min(stacked, forced_index):
+    """torch.min(dim=1) as the reference does, or -- for tie analysis in the tests -- the
+    same reduction with the selected channel imposed (gather), which has the identical
+    backward (gradient to the selected channel only)."""
+    if forced_index is None:
+        return torch.min(stacked, dim=1)
+    idx = forced_index.to(torch.int64)
+    return stacked.gather(1, idx.unsqueeze(1)).squeeze(1), idx
+
+
+def photometric_scale(spec: LossSpec, inputs, outputs, scale, noise, forced_index=None):
     """Automask + minimum reprojection for one scale.
     mono/model/mono_fm/net.py:90-106 -> (loss scalar, min_index int64 (B,H,W))."""
     target = inputs[("color", 0, 0)]
@@ -226,7 +236,8 @@ def photometric_scale(spec: LossSpec, inputs, outputs, scale, noise):
     for f in spec.frame_ids[1:]:
         chans.append(reprojection_loss(outputs[("color", f, scale)], target))
     stacked = torch.cat(chans, 1)
-    m, idx = torch.min(stacked, dim=1)
+    outputs[("reproj_stack", scale)] = stacked.detach()       # test-only: lets the tests measure near-ties
+    m, idx = _select_min(stacked, forced_index)
     return m.mean() / len(spec.scales), idx
 
 
@@ -238,50 +249,59 @@ def smooth_scale(spec: LossSpec, inputs, outputs, scale, weight):
     return weight * smooth_loss(disp, inputs[("color", 0, 0)]) / (2 ** scale) / len(spec.scales)
 
 
-def compute_losses_baseline(spec: LossSpec, inputs, outputs, noise):
-    """mono/model/mono_baseline/net.py:51-100 (photometric + automask + smoothness)."""
+def compute_losses_baseline(spec: LossSpec, inputs, outputs, noise, forced=None):
+    """mono/model/mono_baseline/net.py:51-100 (photometric + automask + smoothness).
+    ``forced``: optional {("photo", scale): index map} imposing the arg-min (tests only)."""
     loss = {}
+    forced = forced or {}
     for s in spec.scales:
         images_pred(spec, inputs, outputs, s)
         loss[("min_reconstruct_loss", s)], outputs[("min_index", s)] = \
-            photometric_scale(spec, inputs, outputs, s, noise)
+            photometric_scale(spec, inputs, outputs, s, noise, forced.get(("photo", s)))
+        outputs[("min_index_photo", s)] = outputs[("min_index", s)]
         loss[("smooth_loss", s)] = smooth_scale(spec, inputs, outputs, s, spec.smoothness_weight)
     return loss
 
 
-def compute_losses_fm(spec: LossSpec, inputs, outputs, noise, tgt_feat, src_feats, inv_K_half=None):
+def compute_losses_fm(spec: LossSpec, inputs, outputs, noise, tgt_feat, src_feats, inv_K_half=None,
+                      forced=None):
     """mono/model/mono_fm/net.py:69-133 (adds the feature-metric term, evaluated
     once per scale exactly like the reference does)."""
     loss = {}
+    forced = forced or {}
     for s in spec.scales:
         images_pred(spec, inputs, outputs, s)
         features_pred(spec, inputs, outputs, src_feats, inv_K_half)
-        loss[("min_reconstruct_loss", s)], outputs[("min_index", s)] = \
-            photometric_scale(spec, inputs, outputs, s, noise)
+        loss[("min_reconstruct_loss", s)], outputs[("min_index_photo", s)] = \
+            photometric_scale(spec, inputs, outputs, s, noise, forced.get(("photo", s)))
         per = torch.cat([perceptional_loss(tgt_feat, outputs[("feature", f, 0)])
                          for f in spec.frame_ids[1:]], 1)
-        m, outputs[("min_index", s)] = torch.min(per, dim=1)
+        outputs["feat_stack"] = per.detach()
+        m, outputs[("min_index", s)] = _select_min(per, forced.get("feat"))
         loss[("min_perceptional_loss", s)] = spec.perception_weight * m.mean() / len(spec.scales)
         loss[("smooth_loss", s)] = smooth_scale(spec, inputs, outputs, s, spec.smoothness_weight)
     return loss
 
 
 def compute_losses_inpaint_core(spec: LossSpec, inputs, outputs, noise, tgt_feat, src_feats,
-                                inv_K_half=None):
+                                inv_K_half=None, forced=None):
     """View-synthesis part of mono/model/mono_fm_joint_inpaint/net.py:47-133:
     one un-scaled feature-metric term (:58-70) + per-scale photometric/smooth
     (:96-131).  The autoencoder reconstruction / regularisation terms of that
     method are outside the hot path."""
     loss = {}
+    forced = forced or {}
     features_pred(spec, inputs, outputs, src_feats, inv_K_half)
     per = torch.cat([perceptional_loss(tgt_feat, outputs[("feature", f, 0)])
                      for f in spec.frame_ids[1:]], 1)
-    m, outputs["min_index"] = torch.min(per, dim=1)
+    outputs["feat_stack"] = per.detach()
+    m, outputs["min_index"] = _select_min(per, forced.get("feat"))
     loss["min_perceptional_loss"] = spec.perception_weight * m.mean()
     for s in spec.scales:
         images_pred(spec, inputs, outputs, s)
         loss[("min_reconstruct_loss", s)], outputs[("min_index", s)] = \
-            photometric_scale(spec, inputs, outputs, s, noise)
+            photometric_scale(spec, inputs, outputs, s, noise, forced.get(("photo", s)))
+        outputs[("min_index_photo", s)] = outputs[("min_index", s)]
         loss[("smooth_loss", s)] = smooth_scale(spec, inputs, outputs, s, spec.smoothness_weight)
     return loss
 

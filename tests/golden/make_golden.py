@@ -23,12 +23,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 CASES = {
     # name: (kind, B, H, W, frames, feat_channels, seed)
+    # "waves": band-limited frames/features (synth._waves) -- strict gradient parity (no derivative kinks)
+    "baseline_waves_b2_64x96": ("baseline", 2, 64, 96, "waves", 0, 1234),
+    "fm_waves_b2_64x96_c8": ("fm", 2, 64, 96, "waves", 8, 1236),
+    "inpaint_waves_b1_96x128_c8": ("inpaint", 1, 96, 128, "waves", 8, 1237),
+    # "smooth": box-filtered noise frames -- realistic, judged with the kink-robust metric
     "baseline_smooth_b2_64x96": ("baseline", 2, 64, 96, "smooth", 0, 1234),
     # 32x64: disp_3 is 2x4, so d_dyy is empty and the reference's smooth_loss is NaN
-    # (mean of an empty tensor) -- kept as the degenerate-shape edge case.
+    # (mean of an empty tensor) -- kept as the degenerate-shape edge case; white-noise frames.
     "baseline_white_b1_32x64": ("baseline", 1, 32, 64, "white", 0, 1235),
-    "fm_smooth_b2_64x96_c8": ("fm", 2, 64, 96, "smooth", 8, 1236),
-    "inpaint_smooth_b1_96x128_c8": ("inpaint", 1, 96, 128, "smooth", 8, 1237),
 }
 
 

@@ -30,7 +30,7 @@ def reference_noise(spec, meta):
     return R.draw_automask_noise(spec, meta["B"])
 
 
-def run_restatement(rec, dtype=torch.float32):
+def run_restatement(rec, dtype=torch.float32, forced=None):
     """Runs oracle.restatement on a golden record -> (loss_dict, outputs, leaves)."""
     meta = rec["meta"]
     spec = spec_from_meta(meta)
@@ -41,16 +41,17 @@ def run_restatement(rec, dtype=torch.float32):
     noise = {s: {f: n.to(dtype) for f, n in d.items()} for s, d in noise.items()}
     kind = meta["kind"]
     if kind == "baseline":
-        loss = R.compute_losses_baseline(spec, inputs, outputs, noise)
+        loss = R.compute_losses_baseline(spec, inputs, outputs, noise, forced=forced)
     else:
         src = {f: leaves[("src_feat", f)] for f in spec.frame_ids[1:]}
         if kind == "fm":
-            loss = R.compute_losses_fm(spec, inputs, outputs, noise, leaves["tgt_feat"], src)
+            loss = R.compute_losses_fm(spec, inputs, outputs, noise, leaves["tgt_feat"], src, forced=forced)
         else:
             loss = {}
             feats = [leaves["tgt_feat"]] + [leaves[("feat_level", i)] for i in range(1, 5)]
             for i, f in enumerate(feats):
                 loss[("feature_regularization_loss", i)] = R.feature_regularization_loss(
                     f, inputs[("color", 0, 0)], spec.extra["dis"], spec.extra["cvt"]) / (2 ** i) / 5
-            loss.update(R.compute_losses_inpaint_core(spec, inputs, outputs, noise, leaves["tgt_feat"], src))
+            loss.update(R.compute_losses_inpaint_core(spec, inputs, outputs, noise, leaves["tgt_feat"], src,
+                                                       forced=forced))
     return loss, outputs, leaves

@@ -1,0 +1,113 @@
+"""ctypes binding of libtdl.so (include/tdl.h).  There is no fallback: if the library is
+missing or a call fails, an exception is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtdl.so")
+
+TDL_MAX_SRC = 4
+TDL_MAX_SCALES = 4
+TDL_ABI_VERSION = 1
+
+_fp = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+
+class PhotoArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("S", C.c_int32), ("nscales", C.c_int32),
+        ("disp_h", C.c_int32 * TDL_MAX_SCALES), ("disp_w", C.c_int32 * TDL_MAX_SCALES),
+        ("automask", C.c_int32), ("disp_norm", C.c_int32), ("align_corners", C.c_int32), ("reserved0", C.c_int32),
+        ("min_depth", C.c_double), ("max_depth", C.c_double),
+        ("photo_coef", C.c_float * TDL_MAX_SCALES), ("smooth_coef", C.c_float * TDL_MAX_SCALES),
+        ("smooth_alpha", C.c_float), ("reserved1", C.c_float),
+        ("noise_seed", C.c_uint64),
+        ("target", _vp), ("src", _vp * TDL_MAX_SRC), ("disp", _vp * TDL_MAX_SCALES),
+        ("P", _vp), ("invK", _vp),
+        ("noise", (_vp * TDL_MAX_SRC) * TDL_MAX_SCALES),
+        ("warped", (_vp * TDL_MAX_SRC) * TDL_MAX_SCALES),
+        ("min_index", _vp * TDL_MAX_SCALES),
+        ("workspace", _vp), ("workspace_bytes", C.c_uint64),
+        ("losses", _vp),
+        ("dlosses", _vp), ("d_disp", _vp * TDL_MAX_SCALES), ("dP", _vp),
+    ]
+
+
+class FeatArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("C", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("S", C.c_int32),
+        ("disp_h", C.c_int32), ("disp_w", C.c_int32), ("align_corners", C.c_int32),
+        ("min_depth", C.c_double), ("max_depth", C.c_double),
+        ("coef", C.c_float), ("reserved0", C.c_float),
+        ("tgt", _vp), ("src", _vp * TDL_MAX_SRC), ("disp", _vp), ("P", _vp), ("invK", _vp),
+        ("warped", _vp * TDL_MAX_SRC), ("min_index", _vp),
+        ("workspace", _vp), ("workspace_bytes", C.c_uint64),
+        ("loss", _vp),
+        ("dloss", _vp), ("d_tgt", _vp), ("d_src", _vp * TDL_MAX_SRC), ("d_disp", _vp), ("dP", _vp),
+    ]
+
+
+class EdgeArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("C", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("alpha", C.c_float), ("first_coef", C.c_float), ("second_coef", C.c_float), ("reserved0", C.c_float),
+        ("feature", _vp), ("image", _vp),
+        ("workspace", _vp), ("workspace_bytes", C.c_uint64),
+        ("loss", _vp), ("dloss", _vp), ("d_feature", _vp),
+    ]
+
+
+EXPORTS = ["tdl_abi_version", "tdl_strerror", "tdl_launch_count",
+           "tdl_photo_ws_bytes", "tdl_photo_fwd", "tdl_photo_bwd",
+           "tdl_feat_ws_bytes", "tdl_feat_fwd", "tdl_feat_bwd",
+           "tdl_edge_ws_bytes", "tdl_edge_smooth_fwd", "tdl_edge_smooth_bwd"]
+
+_lib = None
+
+
+class TdlError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libtdl.so once.  Raises (never falls back) when it is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TdlError(f"{LIB_PATH} not found: build it with __graft_entry__.build() "
+                       "(nvcc, sm_100a); there is no CPU fallback for this path")
+    L = C.CDLL(LIB_PATH)
+    L.tdl_abi_version.restype = C.c_int
+    L.tdl_strerror.restype = C.c_char_p
+    L.tdl_strerror.argtypes = [C.c_int]
+    L.tdl_launch_count.restype = C.c_int
+    L.tdl_launch_count.argtypes = [C.c_char_p]
+    L.tdl_photo_ws_bytes.restype = C.c_uint64
+    L.tdl_photo_ws_bytes.argtypes = [C.c_int32] * 5 + [C.POINTER(C.c_int32)] * 2
+    L.tdl_feat_ws_bytes.restype = C.c_uint64
+    L.tdl_feat_ws_bytes.argtypes = [C.c_int32] * 5
+    L.tdl_edge_ws_bytes.restype = C.c_uint64
+    L.tdl_edge_ws_bytes.argtypes = [C.c_int32] * 4
+    for name, T in (("tdl_photo_fwd", PhotoArgs), ("tdl_photo_bwd", PhotoArgs),
+                    ("tdl_feat_fwd", FeatArgs), ("tdl_feat_bwd", FeatArgs),
+                    ("tdl_edge_smooth_fwd", EdgeArgs), ("tdl_edge_smooth_bwd", EdgeArgs)):
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(T), C.c_void_p]
+    if L.tdl_abi_version() != TDL_ABI_VERSION:
+        raise TdlError(f"libtdl.so ABI {L.tdl_abi_version()} != binding {TDL_ABI_VERSION}: rebuild")
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise TdlError(f"{what} failed ({rc}): {lib().tdl_strerror(rc).decode()}")
+
+
+def launch_count(entry: str) -> int:
+    return lib().tdl_launch_count(entry.encode())

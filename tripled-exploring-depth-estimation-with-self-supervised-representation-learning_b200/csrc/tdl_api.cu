@@ -1,0 +1,301 @@
+// extern "C" entry points of libtdl.so (see include/tdl.h): argument validation,
+// workspace carving and kernel sequencing.  No torch types, no allocation, no host sync.
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include "tdl.h"
+#include "tdl_internal.h"
+
+using namespace tdl;
+
+namespace {
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+inline bool pow2_factor(int big, int small, int* fac) {
+    if (small <= 0 || big % small != 0) return false;
+    const int f = big / small;
+    if (f < 1 || f > 32 || (f & (f - 1)) != 0) return false;
+    *fac = f;
+    return true;
+}
+
+struct PhotoWsLayout {
+    uint64_t acc_off, j_off[TDL_MAX_SCALES], argmin_off, total;
+};
+
+PhotoWsLayout photo_layout(int B, int H, int W, int nscales, const int32_t* dh, const int32_t* dw) {
+    PhotoWsLayout L;
+    uint64_t off = 0;
+    L.acc_off = off;
+    off = align_up(off + (uint64_t)nscales * B * 4 * sizeof(double), 256);
+    for (int s = 0; s < TDL_MAX_SCALES; ++s) {
+        L.j_off[s] = off;
+        if (s < nscales) off = align_up(off + (uint64_t)B * 3 * dh[s] * dw[s] * sizeof(float), 256);
+    }
+    L.argmin_off = off;
+    off = align_up(off + (uint64_t)nscales * B * H * W, 256);
+    L.total = off;
+    return L;
+}
+
+int check_photo(const tdl_photo_args* a, bool bwd, PhotoDev* d) {
+    if (!a) return TDL_ERR_NULL;
+    if (a->S < 1 || a->S > TDL_MAX_SRC || a->nscales < 1 || a->nscales > TDL_MAX_SCALES) return TDL_ERR_COUNT;
+    if (a->B < 1 || a->H < 4 || a->W < 4) return TDL_ERR_SHAPE;
+    if (!a->target || !a->P || !a->invK || !a->workspace || !a->losses) return TDL_ERR_NULL;
+    memset(d, 0, sizeof(*d));
+    d->B = a->B; d->H = a->H; d->W = a->W; d->S = a->S; d->nscales = a->nscales;
+    for (int f = 0; f < a->S; ++f) {
+        if (!a->src[f]) return TDL_ERR_NULL;
+        d->src[f] = a->src[f];
+    }
+    for (int s = 0; s < a->nscales; ++s) {
+        if (!a->disp[s]) return TDL_ERR_NULL;
+        int fy, fx;
+        if (!pow2_factor(a->H, a->disp_h[s], &fy) || !pow2_factor(a->W, a->disp_w[s], &fx) || fy != fx)
+            return TDL_ERR_SHAPE;
+        d->disp[s] = a->disp[s];
+        d->dh[s] = a->disp_h[s]; d->dw[s] = a->disp_w[s]; d->fac[s] = fy;
+        d->sy[s] = (float)a->disp_h[s] / (float)a->H;
+        d->sx[s] = (float)a->disp_w[s] / (float)a->W;
+        d->photo_coef[s] = a->photo_coef[s];
+        for (int f = 0; f < a->S; ++f) {
+            d->noise[s][f] = a->noise[s][f];
+            d->warped[s][f] = a->warped[s][f];
+        }
+        d->min_index[s] = reinterpret_cast<long long*>(a->min_index[s]);
+        if (bwd) {
+            if (!a->d_disp[s]) return TDL_ERR_NULL;
+            d->d_disp[s] = a->d_disp[s];
+        }
+    }
+    if (bwd && (!a->dlosses || !a->dP)) return TDL_ERR_NULL;
+    const PhotoWsLayout L = photo_layout(a->B, a->H, a->W, a->nscales, a->disp_h, a->disp_w);
+    if (a->workspace_bytes < L.total) return TDL_ERR_WORKSPACE;
+    char* ws = static_cast<char*>(a->workspace);
+    d->acc = reinterpret_cast<double*>(ws + L.acc_off);
+    for (int s = 0; s < a->nscales; ++s) d->J[s] = reinterpret_cast<float*>(ws + L.j_off[s]);
+    d->argmin = reinterpret_cast<unsigned char*>(ws + L.argmin_off);
+    d->automask = a->automask != 0;
+    d->align_corners = a->align_corners != 0;
+    d->min_disp = (float)(1.0 / a->max_depth);
+    d->range = (float)(1.0 / a->min_depth - 1.0 / a->max_depth);
+    d->seed = a->noise_seed;
+    d->target = a->target; d->P = a->P; d->invK = a->invK;
+    d->dlosses = a->dlosses; d->dP = a->dP;
+    return TDL_OK;
+}
+
+void photo_smooth_levels(const tdl_photo_args* a, const PhotoDev& d, bool bwd, SmoothDev* sm) {
+    memset(sm, 0, sizeof(*sm));
+    sm->B = a->B;
+    sm->nlevels = a->nscales;
+    for (int s = 0; s < a->nscales; ++s) {
+        SmoothLevel& L = sm->lv[s];
+        L.C = 1; L.h = d.dh[s]; L.w = d.dw[s];
+        L.x = d.disp[s]; L.J = d.J[s];
+        L.acc = d.acc + (size_t)s * a->B * 4; L.acc_stride = 4;
+        L.norm = a->disp_norm != 0;
+        L.alpha = a->smooth_alpha;
+        L.first_coef = a->smooth_coef[s]; L.second_coef = a->smooth_coef[s];
+        if (bwd) {
+            L.dloss = a->dlosses + a->nscales + s;
+            L.dx = a->d_disp[s];
+        }
+    }
+}
+
+#define TDL_CUDA(expr)                       \
+    do {                                     \
+        cudaError_t e__ = (expr);            \
+        if (e__ != cudaSuccess) return (int)e__; \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int tdl_abi_version(void) { return TDL_ABI_VERSION; }
+
+const char* tdl_strerror(int code) {
+    switch (code) {
+        case TDL_OK: return "ok";
+        case TDL_ERR_NULL: return "tdl: a required pointer is NULL";
+        case TDL_ERR_SHAPE: return "tdl: unsupported shape (disp size must divide the image size by a power of two <= 32)";
+        case TDL_ERR_WORKSPACE: return "tdl: workspace too small (see *_ws_bytes)";
+        case TDL_ERR_COUNT: return "tdl: S / nscales / C out of range";
+        case TDL_ERR_NODEVICE: return "tdl: no CUDA device";
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "tdl: unknown error";
+}
+
+int tdl_launch_count(const char* entry) {
+    if (!entry) return 0;
+    if (!strcmp(entry, "tdl_photo_fwd")) return 3;        // photo_fwd, smooth_fwd, finalize
+    if (!strcmp(entry, "tdl_photo_bwd")) return 2;        // smooth_bwd, photo_bwd
+    if (!strcmp(entry, "tdl_feat_fwd")) return 2;         // feat_fwd, finalize
+    if (!strcmp(entry, "tdl_feat_bwd")) return 1;
+    if (!strcmp(entry, "tdl_edge_smooth_fwd")) return 3;  // area pyramid, smooth_fwd, finalize
+    if (!strcmp(entry, "tdl_edge_smooth_bwd")) return 1;
+    return 0;
+}
+
+uint64_t tdl_photo_ws_bytes(int32_t B, int32_t H, int32_t W, int32_t S, int32_t nscales, const int32_t* disp_h,
+                            const int32_t* disp_w) {
+    (void)S;
+    if (B < 1 || H < 1 || W < 1 || nscales < 1 || nscales > TDL_MAX_SCALES || !disp_h || !disp_w) return 0;
+    return photo_layout(B, H, W, nscales, disp_h, disp_w).total;
+}
+
+int tdl_photo_fwd(const tdl_photo_args* a, tdl_stream_t stream) {
+    PhotoDev d;
+    const int rc = check_photo(a, false, &d);
+    if (rc != TDL_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDL_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)a->nscales * a->B * 4 * sizeof(double), st));
+    TDL_CUDA(launch_photo_fwd(d, st));
+    SmoothDev sm;
+    photo_smooth_levels(a, d, false, &sm);
+    TDL_CUDA(launch_smooth_fwd(sm, st));
+    TDL_CUDA(launch_photo_finalize(d, a->photo_coef, a->smooth_coef, a->losses, st));
+    return TDL_OK;
+}
+
+int tdl_photo_bwd(const tdl_photo_args* a, tdl_stream_t stream) {
+    PhotoDev d;
+    const int rc = check_photo(a, true, &d);
+    if (rc != TDL_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDL_CUDA(cudaMemsetAsync(a->dP, 0, (size_t)a->B * a->S * 12 * sizeof(float), st));
+    SmoothDev sm;
+    photo_smooth_levels(a, d, true, &sm);
+    TDL_CUDA(launch_smooth_bwd(sm, st));       // writes d_disp[s] (=), the photometric kernel adds to it
+    TDL_CUDA(launch_photo_bwd(d, st));
+    return TDL_OK;
+}
+
+// ------------------------------------------------------------------------------------ feature-metric
+uint64_t tdl_feat_ws_bytes(int32_t B, int32_t C, int32_t h, int32_t w, int32_t S) {
+    (void)C; (void)S;
+    if (B < 1 || h < 1 || w < 1) return 0;
+    return align_up((uint64_t)B * sizeof(double), 256) + align_up((uint64_t)B * h * w, 256);
+}
+
+static int check_feat(const tdl_feat_args* a, bool bwd, FeatDev* d) {
+    if (!a) return TDL_ERR_NULL;
+    if (a->S < 1 || a->S > TDL_MAX_SRC || a->C < 1) return TDL_ERR_COUNT;
+    if (a->B < 1 || a->h < 2 || a->w < 2 || a->disp_h < 1 || a->disp_w < 1) return TDL_ERR_SHAPE;
+    if (!a->tgt || !a->disp || !a->P || !a->invK || !a->workspace || !a->loss) return TDL_ERR_NULL;
+    if (a->workspace_bytes < tdl_feat_ws_bytes(a->B, a->C, a->h, a->w, a->S)) return TDL_ERR_WORKSPACE;
+    memset(d, 0, sizeof(*d));
+    d->B = a->B; d->C = a->C; d->h = a->h; d->w = a->w; d->S = a->S;
+    d->dh = a->disp_h; d->dw = a->disp_w;
+    d->sy = (float)a->disp_h / (float)a->h;
+    d->sx = (float)a->disp_w / (float)a->w;
+    d->align_corners = a->align_corners != 0;
+    d->min_disp = (float)(1.0 / a->max_depth);
+    d->range = (float)(1.0 / a->min_depth - 1.0 / a->max_depth);
+    d->coef = a->coef;
+    d->tgt = a->tgt; d->disp = a->disp; d->P = a->P; d->invK = a->invK;
+    int n_dsrc = 0;
+    for (int f = 0; f < a->S; ++f) {
+        if (!a->src[f]) return TDL_ERR_NULL;
+        d->src[f] = a->src[f];
+        d->warped[f] = a->warped[f];
+        d->d_src[f] = a->d_src[f];
+        n_dsrc += a->d_src[f] != nullptr;
+    }
+    if (bwd && n_dsrc != 0 && n_dsrc != a->S) return TDL_ERR_NULL;     // all or none
+    d->min_index = reinterpret_cast<long long*>(a->min_index);
+    char* ws = static_cast<char*>(a->workspace);
+    d->acc = reinterpret_cast<double*>(ws);
+    d->argmin = reinterpret_cast<unsigned char*>(ws + align_up((uint64_t)a->B * sizeof(double), 256));
+    d->loss = a->loss;
+    if (bwd) {
+        if (!a->dloss || !a->d_disp || !a->dP) return TDL_ERR_NULL;
+        d->dloss = a->dloss; d->d_tgt = a->d_tgt; d->d_disp = a->d_disp; d->dP = a->dP;
+    }
+    return TDL_OK;
+}
+
+int tdl_feat_fwd(const tdl_feat_args* a, tdl_stream_t stream) {
+    FeatDev d;
+    const int rc = check_feat(a, false, &d);
+    if (rc != TDL_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDL_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)a->B * sizeof(double), st));
+    TDL_CUDA(launch_feat_fwd(d, st));
+    TDL_CUDA(launch_feat_finalize(d, st));
+    return TDL_OK;
+}
+
+int tdl_feat_bwd(const tdl_feat_args* a, tdl_stream_t stream) {
+    FeatDev d;
+    const int rc = check_feat(a, true, &d);
+    if (rc != TDL_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t fbytes = (size_t)a->B * a->C * a->h * a->w * sizeof(float);
+    TDL_CUDA(cudaMemsetAsync(a->dP, 0, (size_t)a->B * a->S * 12 * sizeof(float), st));
+    if (a->disp_h != a->h || a->disp_w != a->w)
+        TDL_CUDA(cudaMemsetAsync(a->d_disp, 0, (size_t)a->B * a->disp_h * a->disp_w * sizeof(float), st));
+    for (int f = 0; f < a->S; ++f)
+        if (a->d_src[f]) TDL_CUDA(cudaMemsetAsync(a->d_src[f], 0, fbytes, st));
+    TDL_CUDA(launch_feat_bwd(d, st));
+    return TDL_OK;
+}
+
+// ------------------------------------------------------------------------------------ edge-aware smoothness
+uint64_t tdl_edge_ws_bytes(int32_t B, int32_t C, int32_t h, int32_t w) {
+    (void)C;
+    if (B < 1 || h < 1 || w < 1) return 0;
+    return align_up((uint64_t)B * 4 * sizeof(double), 256) + align_up((uint64_t)B * 3 * h * w * sizeof(float), 256);
+}
+
+static int check_edge(const tdl_edge_args* a, bool bwd, SmoothDev* sm, float** J) {
+    if (!a) return TDL_ERR_NULL;
+    if (a->B < 1 || a->C < 1) return TDL_ERR_COUNT;
+    int fy, fx;
+    if (!pow2_factor(a->H, a->h, &fy) || !pow2_factor(a->W, a->w, &fx) || fy != fx) return TDL_ERR_SHAPE;
+    if (!a->feature || !a->image || !a->workspace || !a->loss) return TDL_ERR_NULL;
+    if (a->workspace_bytes < tdl_edge_ws_bytes(a->B, a->C, a->h, a->w)) return TDL_ERR_WORKSPACE;
+    if (bwd && (!a->dloss || !a->d_feature)) return TDL_ERR_NULL;
+    char* ws = static_cast<char*>(a->workspace);
+    *J = reinterpret_cast<float*>(ws + align_up((uint64_t)a->B * 4 * sizeof(double), 256));
+    memset(sm, 0, sizeof(*sm));
+    sm->B = a->B;
+    sm->nlevels = 1;
+    SmoothLevel& L = sm->lv[0];
+    L.C = a->C; L.h = a->h; L.w = a->w;
+    L.x = a->feature; L.J = *J;
+    L.acc = reinterpret_cast<double*>(ws); L.acc_stride = 4;
+    L.norm = 0; L.alpha = a->alpha;
+    L.first_coef = a->first_coef; L.second_coef = a->second_coef;
+    L.dloss = a->dloss; L.dx = a->d_feature;
+    return TDL_OK;
+}
+
+int tdl_edge_smooth_fwd(const tdl_edge_args* a, tdl_stream_t stream) {
+    SmoothDev sm;
+    float* J;
+    const int rc = check_edge(a, false, &sm, &J);
+    if (rc != TDL_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDL_CUDA(cudaMemsetAsync(sm.lv[0].acc, 0, (size_t)a->B * 4 * sizeof(double), st));
+    TDL_CUDA(launch_area_pyramid(a->image, a->B, a->H, a->W, J, a->h, a->w, st));
+    TDL_CUDA(launch_smooth_fwd(sm, st));
+    TDL_CUDA(launch_edge_finalize(sm.lv[0].acc, 4, a->B, a->first_coef, a->second_coef, a->h, a->w, a->loss, st));
+    return TDL_OK;
+}
+
+int tdl_edge_smooth_bwd(const tdl_edge_args* a, tdl_stream_t stream) {
+    SmoothDev sm;
+    float* J;
+    const int rc = check_edge(a, true, &sm, &J);
+    if (rc != TDL_OK) return rc;
+    TDL_CUDA(launch_smooth_bwd(sm, static_cast<cudaStream_t>(stream)));
+    return TDL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// Internal launch descriptors shared by tdl_api.cu and the kernel translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tdl.h"
+
+namespace tdl {
+
+struct DepthParamsH {
+    float min_disp, range;
+};
+
+// ---- photometric + smoothness, device-side view of tdl_photo_args -------------
+struct PhotoDev {
+    int B, H, W, S, nscales;
+    int dh[TDL_MAX_SCALES], dw[TDL_MAX_SCALES], fac[TDL_MAX_SCALES];
+    float sy[TDL_MAX_SCALES], sx[TDL_MAX_SCALES];     // dh/H, dw/W (F.interpolate scale)
+    int automask, align_corners;
+    float min_disp, range;
+    uint64_t seed;
+    const float* target;
+    const float* src[TDL_MAX_SRC];
+    const float* disp[TDL_MAX_SCALES];
+    const float* P;
+    const float* invK;
+    const float* noise[TDL_MAX_SCALES][TDL_MAX_SRC];
+    float* warped[TDL_MAX_SCALES][TDL_MAX_SRC];
+    long long* min_index[TDL_MAX_SCALES];
+    // workspace
+    double* acc;                 // [nscales][B][4]: photo sum, disp sum, smooth first, smooth second
+    unsigned char* argmin;       // [nscales][B][H][W]
+    float* J[TDL_MAX_SCALES];    // area-downsampled target (B,3,dh,dw)
+    // backward
+    const float* dlosses;
+    float photo_coef[TDL_MAX_SCALES];
+    float* d_disp[TDL_MAX_SCALES];
+    float* dP;
+};
+
+// ---- edge-aware smoothness over a set of levels (one launch) ---------------------
+struct SmoothLevel {
+    int C, h, w;
+    const float* x;        // (B,C,h,w)
+    const float* J;        // (B,3,h,w) area-downsampled image
+    double* acc;           // per image b: acc[b*stride + 2] += first, acc[b*stride + 3] += second;
+                           //              acc[b*stride + 1] holds sum(x) when norm
+    int acc_stride;
+    int norm;              // divide x by (mean_hw + 1e-7) first (C must be 1)
+    float alpha;
+    float first_coef, second_coef;
+    // backward
+    const float* dloss;    // scalar upstream
+    float* dx;             // (B,C,h,w), overwritten
+};
+
+struct SmoothDev {
+    int B, nlevels;
+    SmoothLevel lv[TDL_MAX_SCALES];
+};
+
+// ---- feature-metric ----------------------------------------------------------------
+struct FeatDev {
+    int B, C, h, w, S;
+    int dh, dw;
+    float sy, sx;
+    int align_corners;
+    float min_disp, range;
+    float coef;
+    const float* tgt;
+    const float* src[TDL_MAX_SRC];
+    const float* disp;
+    const float* P;
+    const float* invK;
+    float* warped[TDL_MAX_SRC];
+    long long* min_index;
+    double* acc;                 // [B]
+    unsigned char* argmin;       // [B][h][w]
+    float* loss;
+    const float* dloss;
+    float* d_tgt;
+    float* d_src[TDL_MAX_SRC];
+    float* d_disp;
+    float* dP;
+};
+
+// launchers (each returns the cudaError_t of its launch)
+cudaError_t launch_photo_fwd(const PhotoDev& p, cudaStream_t st);
+cudaError_t launch_photo_bwd(const PhotoDev& p, cudaStream_t st);
+cudaError_t launch_smooth_fwd(const SmoothDev& p, cudaStream_t st);
+cudaError_t launch_smooth_bwd(const SmoothDev& p, cudaStream_t st);
+cudaError_t launch_area_pyramid(const float* img, int B, int H, int W, float* J, int h, int w, cudaStream_t st);
+cudaError_t launch_photo_finalize(const PhotoDev& p, const float* photo_coef, const float* smooth_coef,
+                                  float* losses, cudaStream_t st);
+cudaError_t launch_feat_fwd(const FeatDev& p, cudaStream_t st);
+cudaError_t launch_feat_finalize(const FeatDev& p, cudaStream_t st);
+cudaError_t launch_feat_bwd(const FeatDev& p, cudaStream_t st);
+cudaError_t launch_edge_finalize(const double* acc, int acc_stride, int B, float first_coef, float second_coef,
+                                 int h, int w, float* loss, cudaStream_t st);
+
+}  // namespace tdl

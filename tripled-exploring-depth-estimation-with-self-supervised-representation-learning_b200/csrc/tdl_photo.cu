@@ -1,0 +1,583 @@
+// Fused photometric view-synthesis loss, forward and backward (sm_100a).
+//
+// Forward  (one CTA = one 32x32 full-resolution tile of one image, ALL scales):
+//   target + source tiles (halo 1, reflect) -> shared memory once; target window
+//   statistics and the identity (automask) reprojection errors are computed once
+//   and reused by every scale; per scale the tile (+halo) is re-projected through
+//   disp_s / P_f, the sources are sampled bilinearly (border) into shared memory,
+//   3x3 SSIM + robust L1 are evaluated with a register sliding window, the
+//   per-pixel minimum / first-argmin over [identity..., warped...] is taken and the
+//   per-image sums are reduced with warp shuffles.  Side products written from the
+//   tile already in shared memory: the warped images, min_index, the u8 argmin mask
+//   (workspace), the area-downsampled target pyramid and the per-image disparity sums
+//   that the smoothness kernel needs.
+// Backward (one CTA = one tile of one image at ONE scale): recomputes the warp with
+//   halo 2, evaluates the SSIM window adjoint, the bilinear-sampling / projection /
+//   back-projection adjoints, reduces dP with shuffles and folds the bilinear
+//   up-sampling adjoint of disp_s inside the tile before touching global memory.
+//
+// Reference behaviour: mono/model/mono_fm/net.py:63-67,90-106,157-170 and
+// mono/model/mono_fm/layers.py:57-107 (see include/tdl.h).
+#include "tdl_common.cuh"
+#include "tdl_internal.h"
+
+namespace tdl {
+
+constexpr int kTW = 32;        // tile width  (one warp lane per column)
+constexpr int kTH = 32;        // tile height
+constexpr int kNT = 256;       // threads per CTA
+constexpr int kR = 4;          // rows per thread (vertical strip)
+static_assert(kTH == (kNT / 32) * kR, "tile / thread mapping");
+
+// ------------------------------------------------------------------------------------------------
+// SSIM + robust-L1 over a vertical strip of kR pixels of one channel.
+// xs / ys point at the channel plane in shared memory with pitch `pitch`; (r, c) is the
+// top-left corner of the 3x3 window of the strip's first pixel.
+// nn.AvgPool2d(3,1) of ATen (CPU and CUDA alike) accumulates the window in row-major order and
+// divides by 9; the same order is used here so that, for identical inputs, the statistics -- and with
+// them the rounding noise that torch.clamp(.., 0, 1) rectifies when SSIM ~ 0 -- are bit-identical.
+TDL_DEV float sum9(const float v[kR + 2][3], int i) {
+    float a = v[i][0];
+    a = __fadd_rn(a, v[i][1]);
+    a = __fadd_rn(a, v[i][2]);
+    a = __fadd_rn(a, v[i + 1][0]);
+    a = __fadd_rn(a, v[i + 1][1]);
+    a = __fadd_rn(a, v[i + 1][2]);
+    a = __fadd_rn(a, v[i + 2][0]);
+    a = __fadd_rn(a, v[i + 2][1]);
+    a = __fadd_rn(a, v[i + 2][2]);
+    return a;
+}
+
+template <int PITCH>
+TDL_DEV void strip_target_stats(const float* __restrict__ ys, int r, int c, float mu_y[kR], float sg_y[kR]) {
+    float y[kR + 2][3], yy[kR + 2][3];
+#pragma unroll
+    for (int j = 0; j < kR + 2; ++j) {
+        const float* yr = ys + (r + j) * PITCH + c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            y[j][k] = yr[k];
+            yy[j][k] = __fmul_rn(yr[k], yr[k]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+        const float m = div9(sum9(y, i));
+        mu_y[i] = m;
+        sg_y[i] = __fsub_rn(div9(sum9(yy, i)), __fmul_rn(m, m));                       // layers.py:102
+    }
+}
+
+TDL_DEV float ssim_value(float mu_x, float mu_y, float sg_x, float sg_y, float sg_xy) {
+    const float n = __fmul_rn(__fadd_rn(__fmul_rn(__fmul_rn(2.f, mu_x), mu_y), kSsimC1),
+                              __fadd_rn(__fmul_rn(2.f, sg_xy), kSsimC2));                  // layers.py:104
+    const float d = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(mu_x, mu_x), __fmul_rn(mu_y, mu_y)), kSsimC1),
+                              __fadd_rn(__fadd_rn(sg_x, sg_y), kSsimC2));                  // layers.py:105
+    const float v = __fdiv_rn(__fsub_rn(1.f, __fdiv_rn(n, d)), 2.f);                       // layers.py:106
+    return fminf(fmaxf(v, 0.f), 1.f);
+}
+
+template <int PITCH>
+TDL_DEV void strip_ssim_l1(const float* __restrict__ xs, const float* __restrict__ ys, int r, int c,
+                           const float mu_y[kR], const float sg_y[kR], float ssim_acc[kR], float l1_acc[kR]) {
+    float x[kR + 2][3], xx[kR + 2][3], xy[kR + 2][3];
+    float yc[kR];
+#pragma unroll
+    for (int j = 0; j < kR + 2; ++j) {
+        const float* xr = xs + (r + j) * PITCH + c;
+        const float* yr = ys + (r + j) * PITCH + c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float xv = xr[k], yv = yr[k];
+            x[j][k] = xv;
+            xx[j][k] = __fmul_rn(xv, xv);
+            xy[j][k] = __fmul_rn(xv, yv);
+            if (k == 1 && j >= 1 && j <= kR) yc[j - 1] = yv;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+        const float mu_x = div9(sum9(x, i));
+        const float sg_x = __fsub_rn(div9(sum9(xx, i)), __fmul_rn(mu_x, mu_x));
+        const float sg_xy = __fsub_rn(div9(sum9(xy, i)), __fmul_rn(mu_x, mu_y[i]));
+        ssim_acc[i] += ssim_value(mu_x, mu_y[i], sg_x, sg_y[i], sg_xy);
+        const float df = __fsub_rn(yc[i], x[i + 1][1]);                                    // net.py:57
+        l1_acc[i] += __fsqrt_rn(__fadd_rn(__fmul_rn(df, df), kL1Eps2));
+    }
+}
+
+// rho = 0.85 * mean_c SSIM + 0.15 * mean_c L1 for the strip (net.py:63-67)
+template <int PITCH>
+TDL_DEV void strip_reprojection(const float* __restrict__ pred3, const float* __restrict__ tgt3, int plane,
+                                int r, int c, const float mu_y[3][kR], const float sg_y[3][kR], float rho[kR]) {
+    float sa[kR], la[kR];
+#pragma unroll
+    for (int i = 0; i < kR; ++i) sa[i] = la[i] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+        strip_ssim_l1<PITCH>(pred3 + ch * plane, tgt3 + ch * plane, r, c, mu_y[ch], sg_y[ch], sa, la);
+#pragma unroll
+    for (int i = 0; i < kR; ++i)
+        rho[i] = __fadd_rn(__fmul_rn(0.85f, __fdiv_rn(sa[i], 3.f)), __fmul_rn(0.15f, __fdiv_rn(la[i], 3.f)));
+}
+
+TDL_DEV float automask_noise(const PhotoDev& p, int s, int f, int b, size_t pix, size_t HW) {
+    const float* n = p.noise[s][f];
+    if (n) return __ldg(n + (size_t)b * HW + pix);
+    const unsigned long long idx = (unsigned long long)b * HW + pix;
+    const uint4 r = philox4x32(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)(s * TDL_MAX_SRC + f), 0u),
+                               make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+    return box_muller(r.x, r.y).x;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(kNT, 2) photo_fwd_kernel(const PhotoDev p) {
+    constexpr int PW = kTW + 2, PH = kTH + 2, PLANE = PW * PH;
+    extern __shared__ float smem[];
+    float* s_tgt = smem;                  // [3][PH][PW]
+    float* s_buf = smem + 3 * PLANE;      // [S][3][PH][PW]: sources (identity), then warped per scale
+    __shared__ float s_red[32];
+    __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int b = blockIdx.z, tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
+    const int H = p.H, W = p.W;
+    const size_t HW = (size_t)H * W;
+
+    if (tid < S * 12) s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
+    if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
+    const float* s_iK = s_cam + TDL_MAX_SRC * 12;
+
+    // ---- phase 0: target and source tiles with a reflected halo of 1
+    {
+        const float* tb = p.target + (size_t)b * 3 * HW;
+        for (int i = tid; i < PLANE; i += kNT) {
+            const int r = i / PW, c = i - r * PW;
+            const size_t o = (size_t)reflect1(ty0 - 1 + r, H) * W + reflect1(tx0 - 1 + c, W);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) s_tgt[ch * PLANE + i] = __ldg(tb + ch * HW + o);
+#pragma unroll
+            for (int f = 0; f < S; ++f) {
+                const float* sb = p.src[f] + (size_t)b * 3 * HW;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) s_buf[(f * 3 + ch) * PLANE + i] = __ldg(sb + ch * HW + o);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- area-downsampled target pyramid (F.interpolate(mode='area'), net.py:259) and disparity sums
+    for (int s = 0; s < p.nscales; ++s) {
+        const int fac = p.fac[s], cells = kTW / fac, h = p.dh[s], w = p.dw[s];
+        const int cj0 = ty0 / fac, ci0 = tx0 / fac;
+        const float inv = 1.f / (float)(fac * fac);
+        float dsum = 0.f;
+        for (int i = tid; i < cells * cells * 3; i += kNT) {
+            const int ch = i / (cells * cells), rem = i - ch * cells * cells;
+            const int cj = rem / cells, ci = rem - cj * cells;
+            if (cj0 + cj < h && ci0 + ci < w) {
+                const float* base = s_tgt + ch * PLANE + (1 + cj * fac) * PW + 1 + ci * fac;
+                float acc = 0.f;
+                for (int dy = 0; dy < fac; ++dy)
+                    for (int dx = 0; dx < fac; ++dx) acc += base[dy * PW + dx];
+                const size_t o = (((size_t)b * 3 + ch) * h + cj0 + cj) * w + ci0 + ci;
+                p.J[s][o] = acc * inv;
+                if (ch == 0) dsum += __ldg(p.disp[s] + ((size_t)b * h + cj0 + cj) * w + ci0 + ci);
+            }
+        }
+        dsum = block_sum(dsum, s_red);
+        if (tid == 0) atomicAdd(p.acc + ((size_t)s * p.B + b) * 4 + 1, (double)dsum);
+    }
+
+    // ---- per-thread strip: column `lane`, rows wrp*kR .. wrp*kR+kR-1 of the tile
+    const int r0 = wrp * kR;
+    const int gx = tx0 + lane;
+    float mu_y[3][kR], sg_y[3][kR];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) strip_target_stats<PW>(s_tgt + ch * PLANE, r0, lane, mu_y[ch], sg_y[ch]);
+
+    float rho_id[S][kR];
+    if (p.automask) {
+#pragma unroll
+        for (int f = 0; f < S; ++f)
+            strip_reprojection<PW>(s_buf + f * 3 * PLANE, s_tgt, PLANE, r0, lane, mu_y, sg_y, rho_id[f]);
+    }
+    __syncthreads();
+
+    const DepthParams dp{p.min_disp, p.range};
+
+    for (int s = 0; s < p.nscales; ++s) {
+        // ---- phase A: re-project the tile (+halo) through disp_s and sample every source
+        {
+            const int h = p.dh[s], w = p.dw[s];
+            const float* db = p.disp[s] + (size_t)b * h * w;
+            for (int i = tid; i < PLANE; i += kNT) {
+                const int r = i / PW, c = i - r * PW;
+                const int py = reflect1(ty0 - 1 + r, H), px = reflect1(tx0 - 1 + c, W);
+                const UpTap ut = up_tap(py, px, p.sy[s], p.sx[s], h, w);
+                const Geo g = backproject(up_value(db, w, ut), dp, s_iK, px, py);
+#pragma unroll
+                for (int f = 0; f < S; ++f) {
+                    const Proj pr = project<false>(g, s_cam + f * 12, H, W, p.align_corners);
+                    const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
+                    const float* sb = p.src[f] + (size_t)b * 3 * HW;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) s_buf[(f * 3 + ch) * PLANE + i] = bilin_sample(sb + ch * HW, W, bt);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase B: reprojection errors, automask, minimum over frames
+        float best[kR];
+        int arg[kR];
+#pragma unroll
+        for (int i = 0; i < kR; ++i) {
+            best[i] = 0.f;
+            arg[i] = -1;
+        }
+        int chan = 0;
+        if (p.automask) {
+#pragma unroll
+            for (int f = 0; f < S; ++f) {
+#pragma unroll
+                for (int i = 0; i < kR; ++i) {
+                    const int gy = ty0 + r0 + i;
+                    float v = rho_id[f][i];
+                    if (gx < W && gy < H)
+                        v = __fadd_rn(v, __fmul_rn(automask_noise(p, s, f, b, (size_t)gy * W + gx, HW), 1e-5f));
+                    if (arg[i] < 0 || v < best[i]) {
+                        best[i] = v;
+                        arg[i] = chan;
+                    }
+                }
+                ++chan;
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < S; ++f) {
+            float rho[kR];
+            strip_reprojection<PW>(s_buf + f * 3 * PLANE, s_tgt, PLANE, r0, lane, mu_y, sg_y, rho);
+#pragma unroll
+            for (int i = 0; i < kR; ++i) {
+                if (arg[i] < 0 || rho[i] < best[i]) {
+                    best[i] = rho[i];
+                    arg[i] = chan;
+                }
+            }
+            ++chan;
+        }
+
+        // ---- outputs of this scale
+        float lsum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kR; ++i) {
+            const int gy = ty0 + r0 + i;
+            if (gx < W && gy < H) {
+                const size_t pix = (size_t)gy * W + gx;
+                lsum += best[i];
+                p.argmin[((size_t)s * p.B + b) * HW + pix] = (unsigned char)arg[i];
+                if (p.min_index[s]) p.min_index[s][(size_t)b * HW + pix] = arg[i];
+#pragma unroll
+                for (int f = 0; f < S; ++f) {
+                    float* wo = p.warped[s][f];
+                    if (wo) {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch)
+                            wo[((size_t)b * 3 + ch) * HW + pix] =
+                                s_buf[(f * 3 + ch) * PLANE + (r0 + 1 + i) * PW + lane + 1];
+                    }
+                }
+            }
+        }
+        lsum = block_sum(lsum, s_red);     // also the barrier that frees s_buf for the next scale
+        if (tid == 0) atomicAdd(p.acc + ((size_t)s * p.B + b) * 4 + 0, (double)lsum);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward.
+template <int S>
+__global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
+    constexpr int QW = kTW + 4, QH = kTH + 4, QPLANE = QW * QH;       // halo 2
+    constexpr int PW = kTW + 2, PH = kTH + 2;                           // window centres: halo 1
+    extern __shared__ float smem[];
+    float* s_tgt = smem;                         // [3][QPLANE]
+    float* s_wrp = s_tgt + 3 * QPLANE;           // [S][3][QPLANE]
+    float* s_coef = s_wrp + S * 3 * QPLANE;      // [3 ch][3 coef][QPLANE]
+    unsigned char* s_mask = reinterpret_cast<unsigned char*>(s_coef + 9 * QPLANE);   // [QPLANE]
+    __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
+    __shared__ float s_dP[TDL_MAX_SRC * 12];
+    __shared__ int s_tx0[kTW], s_tx1[kTW], s_ty0[kTH], s_ty1[kTH];
+    __shared__ float s_tlx[kTW], s_tly[kTH];
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int b = blockIdx.z / p.nscales, s = blockIdx.z - b * p.nscales;
+    const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
+    const int H = p.H, W = p.W;
+    const size_t HW = (size_t)H * W;
+    const int h = p.dh[s], w = p.dw[s];
+    const float up = __ldg(p.dlosses + s) * p.photo_coef[s] / ((float)p.B * (float)H * (float)W);
+
+    if (tid < S * 12) {
+        s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
+        s_dP[tid] = 0.f;
+    }
+    if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
+    const float* s_iK = s_cam + TDL_MAX_SRC * 12;
+    if (tid < kTW) up_index(tx0 + tid, p.sx[s], w, s_tx0[tid], s_tx1[tid], s_tlx[tid]);
+    if (tid >= 32 && tid < 32 + kTH) up_index(ty0 + tid - 32, p.sy[s], h, s_ty0[tid - 32], s_ty1[tid - 32], s_tly[tid - 32]);
+    __syncthreads();
+
+    const DepthParams dp{p.min_disp, p.range};
+    const float* db = p.disp[s] + (size_t)b * h * w;
+    const unsigned char* am = p.argmin + ((size_t)s * p.B + b) * HW;
+
+    // ---- phase 1: target, argmin mask and re-computed warps over the tile with halo 2
+    {
+        const float* tb = p.target + (size_t)b * 3 * HW;
+        for (int i = tid; i < QPLANE; i += kNT) {
+            const int r = i / QW, c = i - r * QW;
+            const int ry = ty0 - 2 + r, rx = tx0 - 2 + c;
+            const bool inside = ry >= 0 && ry < H && rx >= 0 && rx < W;
+            const int py = reflect1(ry, H), px = reflect1(rx, W);
+            const size_t o = (size_t)py * W + px;
+            s_mask[i] = inside ? am[o] : (unsigned char)255;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) s_tgt[ch * QPLANE + i] = __ldg(tb + ch * HW + o);
+            const UpTap ut = up_tap(py, px, p.sy[s], p.sx[s], h, w);
+            const Geo g = backproject(up_value(db, w, ut), dp, s_iK, px, py);
+#pragma unroll
+            for (int f = 0; f < S; ++f) {
+                const Proj pr = project<false>(g, s_cam + f * 12, H, W, p.align_corners);
+                const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
+                const float* sb = p.src[f] + (size_t)b * 3 * HW;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) s_wrp[(f * 3 + ch) * QPLANE + i] = bilin_sample(sb + ch * HW, W, bt);
+            }
+        }
+    }
+    __syncthreads();
+
+    const int r0 = wrp * kR;
+    const int gx = tx0 + lane;
+    float gd[kR];                       // d loss / d (up-sampled disparity) of this thread's pixels
+#pragma unroll
+    for (int i = 0; i < kR; ++i) gd[i] = 0.f;
+    const float g_ssim = up * 0.85f / 3.f, g_l1 = up * 0.15f / 3.f;
+
+#pragma unroll 1
+    for (int f = 0; f < S; ++f) {
+        const int chan = (p.automask ? S : 0) + f;
+        // ---- phase 2: SSIM adjoint coefficients of every window centre (tile + halo 1)
+        for (int i = tid; i < PH * PW; i += kNT) {
+            const int r = i / PW, c = i - r * PW;
+            const int q = (r + 1) * QW + (c + 1);
+            const bool sel = s_mask[q] == chan;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float cA = 0.f, cB = 0.f, cC = 0.f;
+                if (sel) {
+                    const float* xs = s_wrp + (f * 3 + ch) * QPLANE + q;
+                    const float* ys = s_tgt + ch * QPLANE + q;
+                    float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy) {          // row-major, like the forward (sum9)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const float xv = xs[dy * QW + dx], yv = ys[dy * QW + dx];
+                            const bool first = dy == -1 && dx == -1;
+                            sx = first ? xv : __fadd_rn(sx, xv);
+                            sy = first ? yv : __fadd_rn(sy, yv);
+                            sxx = first ? __fmul_rn(xv, xv) : __fadd_rn(sxx, __fmul_rn(xv, xv));
+                            syy = first ? __fmul_rn(yv, yv) : __fadd_rn(syy, __fmul_rn(yv, yv));
+                            sxy = first ? __fmul_rn(xv, yv) : __fadd_rn(sxy, __fmul_rn(xv, yv));
+                        }
+                    }
+                    const float mu_x = div9(sx), mu_y = div9(sy);
+                    const float sg_x = __fsub_rn(div9(sxx), __fmul_rn(mu_x, mu_x));
+                    const float sg_y = __fsub_rn(div9(syy), __fmul_rn(mu_y, mu_y));
+                    const float sg_xy = __fsub_rn(div9(sxy), __fmul_rn(mu_x, mu_y));
+                    const float n1 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, mu_x), mu_y), kSsimC1);
+                    const float n2 = __fadd_rn(__fmul_rn(2.f, sg_xy), kSsimC2);
+                    const float d1 = __fadd_rn(__fadd_rn(__fmul_rn(mu_x, mu_x), __fmul_rn(mu_y, mu_y)), kSsimC1);
+                    const float d2 = __fadd_rn(__fadd_rn(sg_x, sg_y), kSsimC2);
+                    const float n = __fmul_rn(n1, n2), d = __fmul_rn(d1, d2);
+                    const float v = __fdiv_rn(__fsub_rn(1.f, __fdiv_rn(n, d)), 2.f);   // identical to the forward
+                    if (v >= 0.f && v <= 1.f) {                           // clamp passes gradient inside [0,1]
+                        const float rd = 1.f / d;
+                        const float gmu = (-mu_y * (n2 - n1) + (n * rd) * mu_x * (d2 - d1)) * rd;
+                        const float ga = n * d1 * 0.5f * rd * rd;
+                        const float gc = -n1 * rd;
+                        const float k = g_ssim * (1.f / 9.f);
+                        cA = k * gmu;
+                        cB = k * ga;
+                        cC = k * gc;
+                    }
+                }
+                s_coef[(ch * 3 + 0) * QPLANE + q] = cA;
+                s_coef[(ch * 3 + 1) * QPLANE + q] = cB;
+                s_coef[(ch * 3 + 2) * QPLANE + q] = cC;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 3: gather the window adjoint, chain through sampling and projection
+        float aP[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) aP[k] = 0.f;
+        const float* Pf = s_cam + f * 12;
+#pragma unroll
+        for (int i = 0; i < kR; ++i) {
+            const int gy = ty0 + r0 + i;
+            if (gx < W && gy < H) {
+                const int q = (r0 + i + 2) * QW + lane + 2;
+                // reflect-padding multiplicity of window centre p for pixel q (1-D each)
+                float mxw[3], myw[3];
+#pragma unroll
+                for (int d = -1; d <= 1; ++d) {
+                    const int pxx = gx + d, pyy = gy + d;
+                    mxw[d + 1] = 1.f + ((pxx == 0 && gx == 1) ? 1.f : 0.f) + ((pxx == W - 1 && gx == W - 2) ? 1.f : 0.f);
+                    myw[d + 1] = 1.f + ((pyy == 0 && gy == 1) ? 1.f : 0.f) + ((pyy == H - 1 && gy == H - 2) ? 1.f : 0.f);
+                }
+                const UpTap ut{s_ty0[r0 + i], s_ty1[r0 + i], s_tx0[lane], s_tx1[lane], s_tly[r0 + i], s_tlx[lane]};
+                const Geo g = backproject(up_value(db, w, ut), dp, s_iK, gx, gy);
+                const Proj pr = project<true>(g, Pf, H, W, p.align_corners);
+                const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
+                const float* sb = p.src[f] + (size_t)b * 3 * HW;
+                const bool sel = s_mask[q] == chan;
+                float gix = 0.f, giy = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    float sA = 0.f, sB = 0.f, sC = 0.f;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const float m = mxw[dx + 1] * myw[dy + 1];
+                            const int qq = q + dy * QW + dx;
+                            sA += m * s_coef[(ch * 3 + 0) * QPLANE + qq];
+                            sB += m * s_coef[(ch * 3 + 1) * QPLANE + qq];
+                            sC += m * s_coef[(ch * 3 + 2) * QPLANE + qq];
+                        }
+                    const float xv = s_wrp[(f * 3 + ch) * QPLANE + q], yv = s_tgt[ch * QPLANE + q];
+                    float G = sA + 2.f * xv * sB + yv * sC;
+                    if (sel) {
+                        const float df = xv - yv;
+                        G += g_l1 * df / sqrtf(df * df + kL1Eps2);
+                    }
+                    float dix, diy;
+                    bilin_sample_grad(sb + ch * HW, W, bt, dix, diy);
+                    gix += G * dix;
+                    giy += G * diy;
+                }
+                const float gu = gix * pr.mx, gv = giy * pr.my;
+                const float rz = 1.f / pr.z;
+                const float gp0 = gu * rz, gp1 = gv * rz, gp2 = -(gu * pr.u + gv * pr.v) * rz;
+                aP[0] += gp0 * g.X0; aP[1] += gp0 * g.X1; aP[2] += gp0 * g.X2; aP[3] += gp0;
+                aP[4] += gp1 * g.X0; aP[5] += gp1 * g.X1; aP[6] += gp1 * g.X2; aP[7] += gp1;
+                aP[8] += gp2 * g.X0; aP[9] += gp2 * g.X1; aP[10] += gp2 * g.X2; aP[11] += gp2;
+                const float gX0 = Pf[0] * gp0 + Pf[4] * gp1 + Pf[8] * gp2;
+                const float gX1 = Pf[1] * gp0 + Pf[5] * gp1 + Pf[9] * gp2;
+                const float gX2 = Pf[2] * gp0 + Pf[6] * gp1 + Pf[10] * gp2;
+                const float gD = gX0 * g.r0 + gX1 * g.r1 + gX2 * g.r2;
+                gd[i] += -p.range * g.D * g.D * gD;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const float v = warp_sum(aP[k]);
+            if (lane == 0) atomicAdd(&s_dP[f * 12 + k], v);
+        }
+        __syncthreads();          // s_coef is rewritten by the next source frame
+    }
+
+    // ---- phase 4: adjoint of the bilinear up-sampling of disp_s, folded inside the tile
+    float* s_g = s_coef;                        // [kTH][kTW]
+    float* s_t = s_coef + kTH * kTW;            // [kTH][kTW + 2]
+#pragma unroll
+    for (int i = 0; i < kR; ++i) s_g[(r0 + i) * kTW + lane] = gd[i];
+    if (tid < S * 12) atomicAdd(p.dP + ((size_t)b * S) * 12 + tid, s_dP[tid]);
+    __syncthreads();
+    const int ilo = s_tx0[0], ihi = s_tx1[kTW - 1], ni = ihi - ilo + 1;       // <= kTW + 1
+    const int jlo = s_ty0[0], jhi = s_ty1[kTH - 1], nj = jhi - jlo + 1;
+    constexpr int TP = kTW + 2;
+    for (int e = tid; e < kTH * ni; e += kNT) {
+        const int y = e / ni, ii = e - y * ni, gi = ilo + ii;
+        float acc = 0.f;
+        for (int x = 0; x < kTW; ++x) {
+            const float gval = s_g[y * kTW + x];
+            if (s_tx0[x] == gi) acc += (1.f - s_tlx[x]) * gval;
+            if (s_tx1[x] == gi) acc += s_tlx[x] * gval;
+        }
+        s_t[y * TP + ii] = acc;
+    }
+    __syncthreads();
+    float* dd = p.d_disp[s] + (size_t)b * h * w;
+    for (int e = tid; e < nj * ni; e += kNT) {
+        const int jj = e / ni, ii = e - jj * ni, gj = jlo + jj;
+        float acc = 0.f;
+        for (int y = 0; y < kTH; ++y) {
+            const float tv = s_t[y * TP + ii];
+            if (s_ty0[y] == gj) acc += (1.f - s_tly[y]) * tv;
+            if (s_ty1[y] == gj) acc += s_tly[y] * tv;
+        }
+        if (acc != 0.f) atomicAdd(dd + (size_t)gj * w + ilo + ii, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int S>
+static cudaError_t launch_fwd_t(const PhotoDev& p, cudaStream_t st) {
+    constexpr int PLANE = (kTW + 2) * (kTH + 2);
+    const size_t smem = (size_t)(3 + 3 * S) * PLANE * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(photo_fwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((p.W + kTW - 1) / kTW, (p.H + kTH - 1) / kTH, p.B);
+    photo_fwd_kernel<S><<<grid, kNT, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int S>
+static cudaError_t launch_bwd_t(const PhotoDev& p, cudaStream_t st) {
+    constexpr int QPLANE = (kTW + 4) * (kTH + 4);
+    const size_t smem = (size_t)(3 + 3 * S + 9) * QPLANE * sizeof(float) + QPLANE;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(photo_bwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((p.W + kTW - 1) / kTW, (p.H + kTH - 1) / kTH, p.B * p.nscales);
+    photo_bwd_kernel<S><<<grid, kNT, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_photo_fwd(const PhotoDev& p, cudaStream_t st) {
+    switch (p.S) {
+        case 1: return launch_fwd_t<1>(p, st);
+        case 2: return launch_fwd_t<2>(p, st);
+        case 3: return launch_fwd_t<3>(p, st);
+        case 4: return launch_fwd_t<4>(p, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_photo_bwd(const PhotoDev& p, cudaStream_t st) {
+    switch (p.S) {
+        case 1: return launch_bwd_t<1>(p, st);
+        case 2: return launch_bwd_t<2>(p, st);
+        case 3: return launch_bwd_t<3>(p, st);
+        case 4: return launch_bwd_t<4>(p, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tdl

@@ -1,0 +1,196 @@
+"""Host-side mirror of the reference's loss methods, backed by the fused kernels.
+
+``ViewSynthesisLossMixin`` gives a net class the reference's method surface
+
+    compute_losses(inputs, outputs[, features]) -> loss_dict
+    generate_images_pred(inputs, outputs, scale) -> outputs
+    generate_features_pred(inputs, outputs)       -> outputs
+
+with the same ``inputs`` / ``outputs`` / ``loss_dict`` keys, weights and divisions as
+    mono/model/mono_baseline/net.py:51-100      (Baseline)
+    mono/model/mono_fm/net.py:69-133            (mono_fm)
+    mono/model/mono_fm_joint_inpaint/net.py:47-133 (TripleD family, view-synthesis part)
+but evaluates them with one fused CUDA pass over all scales instead of ~150 eager
+kernels per scale.  The mixin owns no parameters or buffers, so checkpoints stay
+compatible with the reference's state-dict keys.
+
+Automask tie-break noise (net.py:94).  The reference draws ``torch.randn`` on the CPU
+per scale and source frame and copies it to the GPU.  ``noise_mode``:
+    "philox"    (default) counter-based N(0,1) inside the kernel, no memory traffic;
+    "reference" the reference's own draws: torch.randn from the global CPU generator in
+                the same order (scale-major, then frame), then an H2D copy -- bit-parity
+                with the reference's RNG stream;
+    a dict noise[scale][frame_id] of (B,1,H,W) tensors may also be passed per call.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from .geometry import half_res_intrinsics, projection_matrix
+from .ops import (EdgeAwareSmoothness, EdgeConfig, FeatConfig, FeatureMetricLoss, PhotoConfig,
+                  PhotometricSmoothLoss)
+
+
+def _opt_get(opt, name, default=None):
+    if hasattr(opt, "get"):
+        return opt.get(name, default)
+    return getattr(opt, name, default)
+
+
+class ViewSynthesisLossMixin:
+    """Expects ``self.opt`` with the reference's option names (config/cfg_kitti_fm.py:20-38)."""
+
+    noise_mode = "philox"
+    materialize_outputs = True          # write outputs[("color",f,s)] / ("feature",f,0) / ("min_index",s)
+    grid_sample_align_corners = False   # torch >= 1.3 default, which is what the reference runs with today
+    _smooth_weight_key = "smoothness_weight"
+    _noise_calls = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _src_frames(self):
+        return list(self.opt.frame_ids[1:])
+
+    def _pose(self, inputs, outputs, f):
+        return inputs["stereo_T"] if f == "s" else outputs[("cam_T_cam", 0, f)]
+
+    def _stack_P(self, inputs, outputs, K):
+        return torch.stack([projection_matrix(K, self._pose(inputs, outputs, f)) for f in self._src_frames()], 1)
+
+    def _reference_noise(self, scales, batch, device):
+        H, W = self.opt.height, self.opt.width
+        return {s: {f: torch.randn(batch, 1, H, W).to(device, non_blocking=True) for f in self._src_frames()}
+                for s in scales}
+
+    # ------------------------------------------------------------------ fused photometric + smoothness
+    def _photometric(self, inputs, outputs, scales: Sequence[int], noise=None, materialize=None):
+        opt = self.opt
+        frames = self._src_frames()
+        target = inputs[("color", 0, 0)]
+        n = len(opt.scales)
+        if noise is None and opt.automask and self.noise_mode == "reference":
+            noise = self._reference_noise(scales, target.shape[0], target.device)
+        sw = _opt_get(opt, self._smooth_weight_key, 0.0)
+        type(self)._noise_calls += 1
+        cfg = PhotoConfig(
+            n_src=len(frames), n_scales=len(scales),
+            min_depth=float(opt.min_depth), max_depth=float(opt.max_depth),
+            automask=bool(opt.automask), disp_norm=bool(opt.disp_norm),
+            align_corners=self.grid_sample_align_corners,
+            photo_coef=tuple(1.0 / n for _ in scales),
+            smooth_coef=tuple(sw / (2 ** s) / n for s in scales),
+            materialize=self.materialize_outputs if materialize is None else materialize,
+            noise_seed=(torch.initial_seed() * 1000003 + type(self)._noise_calls) & (2 ** 63 - 1),
+            has_noise=noise is not None and bool(opt.automask))
+        P = self._stack_P(inputs, outputs, inputs["K"])
+        invK = inputs["inv_K"][:, :3, :3]
+        tensors = [inputs[("color", f, 0)] for f in frames] + [outputs[("disp", 0, s)] for s in scales]
+        if cfg.has_noise:
+            tensors += [noise[s][f] for s in scales for f in frames]
+        res = PhotometricSmoothLoss.apply(cfg, target, P, invK, *tensors)
+        losses = res[0]
+        if cfg.materialize:
+            k = 1
+            for s in scales:
+                for f in frames:
+                    outputs[("color", f, s)] = res[k]
+                    k += 1
+            for s in scales:
+                outputs[("min_index", s)] = res[k]
+                outputs[("min_index_photo", s)] = res[k]      # survives mono_fm's overwrite (net.py:117)
+                k += 1
+        return losses
+
+    def generate_images_pred(self, inputs, outputs, scale):
+        """mono/model/mono_fm/net.py:157-170.  Stand-alone use warps the sources for ONE scale;
+        the images are produced by the fused kernel and carry no autograd history (gradients
+        flow through compute_losses)."""
+        with torch.no_grad():
+            self._photometric(inputs, outputs, [scale], materialize=True)
+        return outputs
+
+    # ------------------------------------------------------------------ fused feature-metric
+    def _feature_metric(self, inputs, outputs, tgt_f, src_fs: Dict, coef: float, materialize=None):
+        opt = self.opt
+        frames = self._src_frames()
+        Kh, invKh = half_res_intrinsics(inputs["K"])
+        P = self._stack_P(inputs, outputs, Kh)
+        cfg = FeatConfig(n_src=len(frames), min_depth=float(opt.min_depth), max_depth=float(opt.max_depth),
+                         align_corners=self.grid_sample_align_corners, coef=float(coef),
+                         materialize=self.materialize_outputs if materialize is None else materialize)
+        res = FeatureMetricLoss.apply(cfg, tgt_f, outputs[("disp", 0, 0)], P, invKh[:, :3, :3].contiguous(),
+                                      *[src_fs[f] for f in frames])
+        if cfg.materialize:
+            for i, f in enumerate(frames):
+                outputs[("feature", f, 0)] = res[1 + i]
+        return res[0][0], (res[1 + len(frames)] if cfg.materialize else None)
+
+    def _extract(self, img):
+        ext = getattr(self, "extractor", None) or getattr(self, "Encoder")
+        return ext(img)[0]
+
+    def generate_features_pred(self, inputs, outputs):
+        """mono/model/mono_fm/net.py:172-199 (stand-alone: warped features, no autograd history)."""
+        with torch.no_grad():
+            src = {f: self._extract(inputs[("color", f, 0)]) for f in self._src_frames()}
+            tgt = self._extract(inputs[("color", 0, 0)])
+            self._feature_metric(inputs, outputs, tgt, src, 0.0, materialize=True)
+        return outputs
+
+    # ------------------------------------------------------------------ the three loss families
+    def compute_losses_baseline(self, inputs, outputs, noise=None):
+        """mono/model/mono_baseline/net.py:51-100."""
+        scales = list(self.opt.scales)
+        losses = self._photometric(inputs, outputs, scales, noise)
+        loss_dict = {}
+        for i, s in enumerate(scales):
+            loss_dict[("min_reconstruct_loss", s)] = losses[i]
+            loss_dict[("smooth_loss", s)] = losses[len(scales) + i]
+        return loss_dict
+
+    def compute_losses_fm(self, inputs, outputs, noise=None, tgt_f=None, src_fs=None):
+        """mono/model/mono_fm/net.py:69-133.  The reference re-runs generate_features_pred and the
+        extractor inside the scale loop (net.py:85,113); the values are scale-independent, so they are
+        evaluated once and the same loss tensor is returned under every ('min_perceptional_loss', s)."""
+        opt = self.opt
+        scales = list(opt.scales)
+        loss_dict = self.compute_losses_baseline(inputs, outputs, noise)
+        if src_fs is None:
+            src_fs = {f: self._extract(inputs[("color", f, 0)]) for f in self._src_frames()}
+        if tgt_f is None:
+            tgt_f = self._extract(inputs[("color", 0, 0)])
+        per, idx = self._feature_metric(inputs, outputs, tgt_f, src_fs, opt.perception_weight / len(scales))
+        ordered = {}
+        for s in scales:
+            ordered[("min_reconstruct_loss", s)] = loss_dict[("min_reconstruct_loss", s)]
+            ordered[("min_perceptional_loss", s)] = per
+            ordered[("smooth_loss", s)] = loss_dict[("smooth_loss", s)]
+            if idx is not None:
+                outputs[("min_index", s)] = idx        # the reference overwrites it (net.py:117)
+        return ordered
+
+    def compute_losses_joint_core(self, inputs, outputs, features, noise=None, src_fs=None):
+        """View-synthesis part of mono/model/mono_fm_joint_inpaint/net.py:47-133: one un-divided
+        feature-metric term on features[0] (:58-70) and the per-scale photometric / smoothness terms
+        (:96-131), plus get_feature_regularization_loss on the five feature levels (:53-56)."""
+        opt = self.opt
+        loss_dict = {}
+        target = inputs[("color", 0, 0)]
+        if features is not None:
+            for i in range(5):
+                loss_dict[("feature_regularization_loss", i)] = self.get_feature_regularization_loss(
+                    features[i], target) / (2 ** i) / 5
+            if src_fs is None:
+                src_fs = {f: self._extract(inputs[("color", f, 0)]) for f in self._src_frames()}
+            per, idx = self._feature_metric(inputs, outputs, features[0], src_fs, opt.perception_weight)
+            loss_dict["min_perceptional_loss"] = per
+            if idx is not None:
+                outputs["min_index"] = idx
+        loss_dict.update(self.compute_losses_baseline(inputs, outputs, noise))
+        return loss_dict
+
+    def get_feature_regularization_loss(self, feature, img):
+        """mono/model/mono_fm_joint/net.py:309-330: -dis * first-order + cvt * second-order."""
+        cfg = EdgeConfig(alpha=1.0, first_coef=-float(self.opt.dis), second_coef=float(self.opt.cvt))
+        return EdgeAwareSmoothness.apply(cfg, feature, img)[0]

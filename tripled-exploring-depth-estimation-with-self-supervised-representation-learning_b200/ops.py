@@ -1,0 +1,308 @@
+"""torch.autograd.Functions over the C ABI of libtdl.so.
+
+PyTorch is plumbing here: it owns the device memory and the CUDA stream; every
+number is produced by the hand-written kernels behind include/tdl.h.  Inputs must be
+CUDA tensors -- there is deliberately no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EdgeArgs, FeatArgs, PhotoArgs, TDL_MAX_SCALES, TDL_MAX_SRC
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.TdlError(f"{name}: expected a CUDA tensor (the fused loss has no CPU implementation)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# --------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class PhotoConfig:
+    """Scalar options of tdl_photo_args (config/cfg_kitti_fm.py:20-38 names in comments)."""
+    n_src: int
+    n_scales: int
+    min_depth: float = 0.1              # min_depth
+    max_depth: float = 100.0            # max_depth
+    automask: bool = True               # automask
+    disp_norm: bool = True              # disp_norm
+    align_corners: bool = False         # torch >= 1.3 F.grid_sample default
+    photo_coef: Tuple[float, ...] = ()  # 1/len(scales) per scale
+    smooth_coef: Tuple[float, ...] = () # smoothness_weight / 2**s / len(scales)
+    smooth_alpha: float = 0.5
+    materialize: bool = True            # write outputs[("color",f,s)] and outputs[("min_index",s)]
+    noise_seed: int = 0                 # Philox seed when no noise tensors are passed
+    has_noise: bool = False
+
+
+class PhotometricSmoothLoss(torch.autograd.Function):
+    """losses[0:n] = min-reprojection loss per scale, losses[n:2n] = smoothness per scale.
+
+    forward(cfg, target, P, invK, *src[S], *disp[n], *noise[n*S]?) ->
+        (losses, *warped[n*S], *min_index[n])      (warped / min_index only if cfg.materialize)
+    """
+
+    @staticmethod
+    def forward(ctx, cfg: PhotoConfig, target, P, invK, *tensors):
+        L = _lib.lib()
+        S, n = cfg.n_src, cfg.n_scales
+        if not (1 <= S <= TDL_MAX_SRC and 1 <= n <= TDL_MAX_SCALES):
+            raise _lib.TdlError(f"n_src={S} / n_scales={n} out of range")
+        target = _f32c(target, "target")
+        P = _f32c(P, "P")
+        invK = _f32c(invK, "invK")
+        srcs = [_f32c(t, "src") for t in tensors[:S]]
+        disps = [_f32c(t, "disp") for t in tensors[S:S + n]]
+        noise = [_f32c(t, "noise") for t in tensors[S + n:]] if cfg.has_noise else []
+        if cfg.has_noise and len(noise) != n * S:
+            raise _lib.TdlError("noise: expected n_scales * n_src tensors")
+        B, _, H, W = target.shape
+        if P.shape != (B, S, 3, 4) or invK.shape != (B, 3, 3):
+            raise _lib.TdlError(f"P {tuple(P.shape)} / invK {tuple(invK.shape)}: expected (B,S,3,4) / (B,3,3)")
+        dev = target.device
+        a = PhotoArgs()
+        a.B, a.H, a.W, a.S, a.nscales = B, H, W, S, n
+        dh = (C.c_int32 * TDL_MAX_SCALES)()
+        dw = (C.c_int32 * TDL_MAX_SCALES)()
+        for s, d in enumerate(disps):
+            if d.shape[0] != B or d.shape[1] != 1:
+                raise _lib.TdlError(f"disp[{s}] {tuple(d.shape)}: expected (B,1,h,w)")
+            dh[s], dw[s] = d.shape[2], d.shape[3]
+            a.disp_h[s], a.disp_w[s] = d.shape[2], d.shape[3]
+            a.disp[s] = d.data_ptr()
+            a.photo_coef[s] = cfg.photo_coef[s]
+            a.smooth_coef[s] = cfg.smooth_coef[s]
+        a.automask, a.disp_norm, a.align_corners = int(cfg.automask), int(cfg.disp_norm), int(cfg.align_corners)
+        a.min_depth, a.max_depth = cfg.min_depth, cfg.max_depth
+        a.smooth_alpha = cfg.smooth_alpha
+        a.noise_seed = cfg.noise_seed & 0xFFFFFFFFFFFFFFFF
+        a.target = target.data_ptr()
+        for f, t in enumerate(srcs):
+            if t.shape != target.shape:
+                raise _lib.TdlError("src/target shape mismatch")
+            a.src[f] = t.data_ptr()
+        a.P, a.invK = P.data_ptr(), invK.data_ptr()
+        for i, t in enumerate(noise):
+            a.noise[i // S][i % S] = t.data_ptr()
+        warped, min_index = [], []
+        if cfg.materialize:
+            for s in range(n):
+                for f in range(S):
+                    w = torch.empty_like(target)
+                    warped.append(w)
+                    a.warped[s][f] = w.data_ptr()
+                m = torch.empty((B, H, W), dtype=torch.int64, device=dev)
+                min_index.append(m)
+                a.min_index[s] = m.data_ptr()
+        ws_bytes = L.tdl_photo_ws_bytes(B, H, W, S, n, dh, dw)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        losses = torch.empty(2 * n, dtype=torch.float32, device=dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+        a.losses = losses.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(L.tdl_photo_fwd(C.byref(a), _stream()), "tdl_photo_fwd")
+        ctx.cfg = cfg
+        ctx.save_for_backward(target, P, invK, ws, *srcs, *disps)
+        ctx.mark_non_differentiable(*warped, *min_index)
+        return (losses, *warped, *min_index)
+
+    @staticmethod
+    def backward(ctx, g_losses, *_unused):
+        L = _lib.lib()
+        cfg = ctx.cfg
+        S, n = cfg.n_src, cfg.n_scales
+        target, P, invK, ws = ctx.saved_tensors[:4]
+        srcs = ctx.saved_tensors[4:4 + S]
+        disps = ctx.saved_tensors[4 + S:4 + S + n]
+        B, _, H, W = target.shape
+        a = PhotoArgs()
+        a.B, a.H, a.W, a.S, a.nscales = B, H, W, S, n
+        d_disps = []
+        for s, d in enumerate(disps):
+            a.disp_h[s], a.disp_w[s] = d.shape[2], d.shape[3]
+            a.disp[s] = d.data_ptr()
+            a.photo_coef[s] = cfg.photo_coef[s]
+            a.smooth_coef[s] = cfg.smooth_coef[s]
+            g = torch.empty_like(d)
+            d_disps.append(g)
+            a.d_disp[s] = g.data_ptr()
+        a.automask, a.disp_norm, a.align_corners = int(cfg.automask), int(cfg.disp_norm), int(cfg.align_corners)
+        a.min_depth, a.max_depth = cfg.min_depth, cfg.max_depth
+        a.smooth_alpha = cfg.smooth_alpha
+        a.target = target.data_ptr()
+        for f, t in enumerate(srcs):
+            a.src[f] = t.data_ptr()
+        a.P, a.invK = P.data_ptr(), invK.data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        scratch = torch.empty(2 * n, dtype=torch.float32, device=target.device)
+        a.losses = scratch.data_ptr()
+        g_losses = _f32c(g_losses, "grad")
+        dP = torch.empty_like(P)
+        a.dlosses, a.dP = g_losses.data_ptr(), dP.data_ptr()
+        with torch.cuda.device(target.device):
+            _lib.check(L.tdl_photo_bwd(C.byref(a), _stream()), "tdl_photo_bwd")
+        n_noise = n * S if cfg.has_noise else 0
+        return (None, None, dP, None, *([None] * S), *d_disps, *([None] * n_noise))
+
+
+# --------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class FeatConfig:
+    n_src: int
+    min_depth: float = 0.1
+    max_depth: float = 100.0
+    align_corners: bool = False
+    coef: float = 1e-3                  # perception_weight (/ len(scales) in mono_fm)
+    materialize: bool = True            # write outputs[("feature",f,0)] and the argmin map
+
+
+class FeatureMetricLoss(torch.autograd.Function):
+    """forward(cfg, tgt, disp, P, invK, *src[S]) -> (loss[1], *warped[S], min_index)"""
+
+    @staticmethod
+    def forward(ctx, cfg: FeatConfig, tgt, disp, P, invK, *srcs):
+        L = _lib.lib()
+        S = cfg.n_src
+        tgt = _f32c(tgt, "tgt_feat")
+        disp = _f32c(disp, "disp")
+        P = _f32c(P, "P")
+        invK = _f32c(invK, "invK")
+        srcs = [_f32c(t, "src_feat") for t in srcs]
+        if len(srcs) != S or not 1 <= S <= TDL_MAX_SRC:
+            raise _lib.TdlError("src_feat: wrong number of source frames")
+        B, Cc, h, w = tgt.shape
+        if P.shape != (B, S, 3, 4) or invK.shape != (B, 3, 3):
+            raise _lib.TdlError(f"P {tuple(P.shape)} / invK {tuple(invK.shape)}: expected (B,S,3,4) / (B,3,3)")
+        a = FeatArgs()
+        a.B, a.C, a.h, a.w, a.S = B, Cc, h, w, S
+        a.disp_h, a.disp_w = disp.shape[2], disp.shape[3]
+        a.align_corners = int(cfg.align_corners)
+        a.min_depth, a.max_depth, a.coef = cfg.min_depth, cfg.max_depth, cfg.coef
+        a.tgt, a.disp, a.P, a.invK = tgt.data_ptr(), disp.data_ptr(), P.data_ptr(), invK.data_ptr()
+        warped, extra = [], []
+        for f, t in enumerate(srcs):
+            if t.shape != tgt.shape:
+                raise _lib.TdlError("src_feat/tgt_feat shape mismatch")
+            a.src[f] = t.data_ptr()
+            if cfg.materialize:
+                wv = torch.empty_like(tgt)
+                warped.append(wv)
+                a.warped[f] = wv.data_ptr()
+        if cfg.materialize:
+            mi = torch.empty((B, h, w), dtype=torch.int64, device=tgt.device)
+            extra.append(mi)
+            a.min_index = mi.data_ptr()
+        ws_bytes = L.tdl_feat_ws_bytes(B, Cc, h, w, S)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=tgt.device)
+        loss = torch.empty(1, dtype=torch.float32, device=tgt.device)
+        a.workspace, a.workspace_bytes, a.loss = ws.data_ptr(), ws_bytes, loss.data_ptr()
+        with torch.cuda.device(tgt.device):
+            _lib.check(L.tdl_feat_fwd(C.byref(a), _stream()), "tdl_feat_fwd")
+        ctx.cfg = cfg
+        ctx.save_for_backward(tgt, disp, P, invK, ws, *srcs)
+        ctx.mark_non_differentiable(*warped, *extra)
+        return (loss, *warped, *extra)
+
+    @staticmethod
+    def backward(ctx, g_loss, *_unused):
+        L = _lib.lib()
+        cfg = ctx.cfg
+        S = cfg.n_src
+        tgt, disp, P, invK, ws = ctx.saved_tensors[:5]
+        srcs = ctx.saved_tensors[5:5 + S]
+        B, Cc, h, w = tgt.shape
+        need = ctx.needs_input_grad            # (cfg, tgt, disp, P, invK, *srcs)
+        a = FeatArgs()
+        a.B, a.C, a.h, a.w, a.S = B, Cc, h, w, S
+        a.disp_h, a.disp_w = disp.shape[2], disp.shape[3]
+        a.align_corners = int(cfg.align_corners)
+        a.min_depth, a.max_depth, a.coef = cfg.min_depth, cfg.max_depth, cfg.coef
+        a.tgt, a.disp, a.P, a.invK = tgt.data_ptr(), disp.data_ptr(), P.data_ptr(), invK.data_ptr()
+        for f, t in enumerate(srcs):
+            a.src[f] = t.data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        scratch = torch.empty(1, dtype=torch.float32, device=tgt.device)
+        a.loss = scratch.data_ptr()
+        g_loss = _f32c(g_loss, "grad")
+        d_disp, dP = torch.empty_like(disp), torch.empty_like(P)
+        a.dloss, a.d_disp, a.dP = g_loss.data_ptr(), d_disp.data_ptr(), dP.data_ptr()
+        d_tgt = None
+        if need[1]:
+            d_tgt = torch.empty_like(tgt)
+            a.d_tgt = d_tgt.data_ptr()
+        d_srcs = [None] * S
+        if any(need[5:5 + S]):
+            d_srcs = [torch.empty_like(tgt) for _ in range(S)]
+            for f, t in enumerate(d_srcs):
+                a.d_src[f] = t.data_ptr()
+        with torch.cuda.device(tgt.device):
+            _lib.check(L.tdl_feat_bwd(C.byref(a), _stream()), "tdl_feat_bwd")
+        return (None, d_tgt, d_disp, dP, None, *d_srcs)
+
+
+# --------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class EdgeConfig:
+    alpha: float = 1.0
+    first_coef: float = 1.0
+    second_coef: float = 1.0
+
+
+class EdgeAwareSmoothness(torch.autograd.Function):
+    """get_feature_regularization_loss (mono/model/mono_fm_joint/net.py:309-330) on one level:
+    forward(cfg, feature (B,C,h,w), image (B,3,H,W)) -> loss[1]."""
+
+    @staticmethod
+    def forward(ctx, cfg: EdgeConfig, feature, image):
+        L = _lib.lib()
+        feature = _f32c(feature, "feature")
+        image = _f32c(image, "image")
+        a, ws = EdgeAwareSmoothness._args(L, cfg, feature, image)
+        loss = torch.empty(1, dtype=torch.float32, device=feature.device)
+        a.loss = loss.data_ptr()
+        with torch.cuda.device(feature.device):
+            _lib.check(L.tdl_edge_smooth_fwd(C.byref(a), _stream()), "tdl_edge_smooth_fwd")
+        ctx.cfg = cfg
+        ctx.save_for_backward(feature, image, ws)
+        return loss
+
+    @staticmethod
+    def _args(L, cfg, feature, image, ws=None):
+        B, Cc, h, w = feature.shape
+        a = EdgeArgs()
+        a.B, a.C, a.h, a.w, a.H, a.W = B, Cc, h, w, image.shape[2], image.shape[3]
+        a.alpha, a.first_coef, a.second_coef = cfg.alpha, cfg.first_coef, cfg.second_coef
+        a.feature, a.image = feature.data_ptr(), image.data_ptr()
+        if ws is None:
+            ws = torch.empty(L.tdl_edge_ws_bytes(B, Cc, h, w), dtype=torch.uint8, device=feature.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        return a, ws
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        L = _lib.lib()
+        feature, image, ws = ctx.saved_tensors
+        a, _ = EdgeAwareSmoothness._args(L, ctx.cfg, feature, image, ws)
+        scratch = torch.empty(1, dtype=torch.float32, device=feature.device)
+        g_loss = _f32c(g_loss, "grad")
+        d_feat = torch.empty_like(feature)
+        a.loss, a.dloss, a.d_feature = scratch.data_ptr(), g_loss.data_ptr(), d_feat.data_ptr()
+        with torch.cuda.device(feature.device):
+            _lib.check(L.tdl_edge_smooth_bwd(C.byref(a), _stream()), "tdl_edge_smooth_bwd")
+        return None, d_feat, None
