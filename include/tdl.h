@@ -144,10 +144,22 @@ typedef struct tdl_edge_args {
     float* d_feature;           /* out (B,C,h,w), overwritten, backward only */
 } tdl_edge_args;
 
+/* one row of tdl_profile_end(): device time attributed to one kernel (CUDA events on the launch stream) */
+typedef struct tdl_kernel_time {
+    char name[32];
+    int32_t launches;
+    double total_ms;
+} tdl_kernel_time;
+
 int tdl_abi_version(void);
 const char* tdl_strerror(int code);
 /* number of CUDA kernels (not memsets) one call launches -- used by bench.py's gpu_launches */
 int tdl_launch_count(const char* entry_point);
+
+/* Per-kernel timing for bench.py (not thread-safe; do not use while a CUDA graph is being captured):
+ * between begin and end every kernel / memset the library launches is bracketed by a cudaEvent pair. */
+int tdl_profile_begin(void);
+int tdl_profile_end(tdl_kernel_time* out, int max_entries);
 
 uint64_t tdl_photo_ws_bytes(int32_t B, int32_t H, int32_t W, int32_t S, int32_t nscales,
                             const int32_t* disp_h, const int32_t* disp_w);

@@ -60,7 +60,11 @@ class EdgeArgs(C.Structure):
     ]
 
 
-EXPORTS = ["tdl_abi_version", "tdl_strerror", "tdl_launch_count",
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int32), ("total_ms", C.c_double)]
+
+
+EXPORTS = ["tdl_abi_version", "tdl_strerror", "tdl_launch_count", "tdl_profile_begin", "tdl_profile_end",
            "tdl_photo_ws_bytes", "tdl_photo_fwd", "tdl_photo_bwd",
            "tdl_feat_ws_bytes", "tdl_feat_fwd", "tdl_feat_bwd",
            "tdl_edge_ws_bytes", "tdl_edge_smooth_fwd", "tdl_edge_smooth_bwd"]
@@ -86,6 +90,9 @@ def lib():
     L.tdl_strerror.argtypes = [C.c_int]
     L.tdl_launch_count.restype = C.c_int
     L.tdl_launch_count.argtypes = [C.c_char_p]
+    L.tdl_profile_begin.restype = C.c_int
+    L.tdl_profile_end.restype = C.c_int
+    L.tdl_profile_end.argtypes = [C.POINTER(KernelTime), C.c_int]
     L.tdl_photo_ws_bytes.restype = C.c_uint64
     L.tdl_photo_ws_bytes.argtypes = [C.c_int32] * 5 + [C.POINTER(C.c_int32)] * 2
     L.tdl_feat_ws_bytes.restype = C.c_uint64
@@ -111,3 +118,14 @@ def check(rc, what):
 
 def launch_count(entry: str) -> int:
     return lib().tdl_launch_count(entry.encode())
+
+
+def profile_begin():
+    check(lib().tdl_profile_begin(), "tdl_profile_begin")
+
+
+def profile_end():
+    """-> {kernel name: (launches, total_ms)} measured with CUDA events on the launch stream."""
+    rows = (KernelTime * 64)()
+    n = lib().tdl_profile_end(rows, 64)
+    return {rows[i].name.decode(): (rows[i].launches, rows[i].total_ms) for i in range(n)}

@@ -3,6 +3,10 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include <map>
+#include <string>
+#include <vector>
+
 #include "tdl.h"
 #include "tdl_internal.h"
 
@@ -112,6 +116,50 @@ void photo_smooth_levels(const tdl_photo_args* a, const PhotoDev& d, bool bwd, S
         if (e__ != cudaSuccess) return (int)e__; \
     } while (0)
 
+// ---- optional per-kernel timing (tdl_profile_begin / tdl_profile_end): a cudaEvent pair is recorded on
+// the launch stream around every kernel, so bench.py can attribute device time to kernels without ncu.
+struct ProfRec {
+    const char* name;
+    cudaEvent_t a, b;
+};
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+} g_prof;
+
+struct ProfScope {
+    cudaStream_t st;
+    bool active;
+    ProfScope(const char* name, cudaStream_t s) : st(s), active(g_prof.on) {
+        if (active) {
+            ProfRec r{name, g_prof.get(), g_prof.get()};
+            cudaEventRecord(r.a, st);
+            g_prof.recs.push_back(r);
+        }
+    }
+    ~ProfScope() {
+        if (active) cudaEventRecord(g_prof.recs.back().b, st);
+    }
+};
+
+#define TDL_KERNEL(name, expr)               \
+    do {                                     \
+        ProfScope scope__(name, st);         \
+        cudaError_t e__ = (expr);            \
+        if (e__ != cudaSuccess) return (int)e__; \
+    } while (0)
+
 }  // namespace
 
 extern "C" {
@@ -142,6 +190,40 @@ int tdl_launch_count(const char* entry) {
     return 0;
 }
 
+int tdl_profile_begin(void) {
+    g_prof.on = true;
+    return TDL_OK;
+}
+
+// Synchronises the recorded events, aggregates per kernel name and writes up to `max_entries` rows
+// (name, launches, total milliseconds).  Returns the number of rows; profiling is switched off.
+int tdl_profile_end(tdl_kernel_time* out, int max_entries) {
+    g_prof.on = false;
+    std::map<std::string, std::pair<int, double>> agg;
+    std::vector<std::string> order;
+    for (ProfRec& r : g_prof.recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            if (!agg.count(r.name)) order.push_back(r.name);
+            agg[r.name].first += 1;
+            agg[r.name].second += ms;
+        }
+        g_prof.pool.push_back(r.a);
+        g_prof.pool.push_back(r.b);
+    }
+    g_prof.recs.clear();
+    int n = 0;
+    for (const std::string& k : order) {
+        if (n >= max_entries || !out) break;
+        strncpy(out[n].name, k.c_str(), sizeof(out[n].name) - 1);
+        out[n].name[sizeof(out[n].name) - 1] = 0;
+        out[n].launches = agg[k].first;
+        out[n].total_ms = agg[k].second;
+        ++n;
+    }
+    return n;
+}
+
 uint64_t tdl_photo_ws_bytes(int32_t B, int32_t H, int32_t W, int32_t S, int32_t nscales, const int32_t* disp_h,
                             const int32_t* disp_w) {
     (void)S;
@@ -154,12 +236,12 @@ int tdl_photo_fwd(const tdl_photo_args* a, tdl_stream_t stream) {
     const int rc = check_photo(a, false, &d);
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDL_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)a->nscales * a->B * 4 * sizeof(double), st));
-    TDL_CUDA(launch_photo_fwd(d, st));
+    TDL_KERNEL("memset", cudaMemsetAsync(d.acc, 0, (size_t)a->nscales * a->B * 4 * sizeof(double), st));
+    TDL_KERNEL("photo_fwd", launch_photo_fwd(d, st));
     SmoothDev sm;
     photo_smooth_levels(a, d, false, &sm);
-    TDL_CUDA(launch_smooth_fwd(sm, st));
-    TDL_CUDA(launch_photo_finalize(d, a->photo_coef, a->smooth_coef, a->losses, st));
+    TDL_KERNEL("smooth_fwd", launch_smooth_fwd(sm, st));
+    TDL_KERNEL("photo_finalize", launch_photo_finalize(d, a->photo_coef, a->smooth_coef, a->losses, st));
     return TDL_OK;
 }
 
@@ -168,11 +250,11 @@ int tdl_photo_bwd(const tdl_photo_args* a, tdl_stream_t stream) {
     const int rc = check_photo(a, true, &d);
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDL_CUDA(cudaMemsetAsync(a->dP, 0, (size_t)a->B * a->S * 12 * sizeof(float), st));
+    TDL_KERNEL("memset", cudaMemsetAsync(a->dP, 0, (size_t)a->B * a->S * 12 * sizeof(float), st));
     SmoothDev sm;
     photo_smooth_levels(a, d, true, &sm);
-    TDL_CUDA(launch_smooth_bwd(sm, st));       // writes d_disp[s] (=), the photometric kernel adds to it
-    TDL_CUDA(launch_photo_bwd(d, st));
+    TDL_KERNEL("smooth_bwd", launch_smooth_bwd(sm, st));       // writes d_disp[s] (=), the photometric kernel adds to it
+    TDL_KERNEL("photo_bwd", launch_photo_bwd(d, st));
     return TDL_OK;
 }
 
@@ -225,9 +307,9 @@ int tdl_feat_fwd(const tdl_feat_args* a, tdl_stream_t stream) {
     const int rc = check_feat(a, false, &d);
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDL_CUDA(cudaMemsetAsync(d.acc, 0, (size_t)a->B * sizeof(double), st));
-    TDL_CUDA(launch_feat_fwd(d, st));
-    TDL_CUDA(launch_feat_finalize(d, st));
+    TDL_KERNEL("memset", cudaMemsetAsync(d.acc, 0, (size_t)a->B * sizeof(double), st));
+    TDL_KERNEL("feat_fwd", launch_feat_fwd(d, st));
+    TDL_KERNEL("feat_finalize", launch_feat_finalize(d, st));
     return TDL_OK;
 }
 
@@ -237,12 +319,12 @@ int tdl_feat_bwd(const tdl_feat_args* a, tdl_stream_t stream) {
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t fbytes = (size_t)a->B * a->C * a->h * a->w * sizeof(float);
-    TDL_CUDA(cudaMemsetAsync(a->dP, 0, (size_t)a->B * a->S * 12 * sizeof(float), st));
+    TDL_KERNEL("memset", cudaMemsetAsync(a->dP, 0, (size_t)a->B * a->S * 12 * sizeof(float), st));
     if (a->disp_h != a->h || a->disp_w != a->w)
-        TDL_CUDA(cudaMemsetAsync(a->d_disp, 0, (size_t)a->B * a->disp_h * a->disp_w * sizeof(float), st));
+        TDL_KERNEL("memset", cudaMemsetAsync(a->d_disp, 0, (size_t)a->B * a->disp_h * a->disp_w * sizeof(float), st));
     for (int f = 0; f < a->S; ++f)
-        if (a->d_src[f]) TDL_CUDA(cudaMemsetAsync(a->d_src[f], 0, fbytes, st));
-    TDL_CUDA(launch_feat_bwd(d, st));
+        if (a->d_src[f]) TDL_KERNEL("memset_dsrc", cudaMemsetAsync(a->d_src[f], 0, fbytes, st));
+    TDL_KERNEL("feat_bwd", launch_feat_bwd(d, st));
     return TDL_OK;
 }
 
@@ -282,10 +364,10 @@ int tdl_edge_smooth_fwd(const tdl_edge_args* a, tdl_stream_t stream) {
     const int rc = check_edge(a, false, &sm, &J);
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDL_CUDA(cudaMemsetAsync(sm.lv[0].acc, 0, (size_t)a->B * 4 * sizeof(double), st));
-    TDL_CUDA(launch_area_pyramid(a->image, a->B, a->H, a->W, J, a->h, a->w, st));
-    TDL_CUDA(launch_smooth_fwd(sm, st));
-    TDL_CUDA(launch_edge_finalize(sm.lv[0].acc, 4, a->B, a->first_coef, a->second_coef, a->h, a->w, a->loss, st));
+    TDL_KERNEL("memset", cudaMemsetAsync(sm.lv[0].acc, 0, (size_t)a->B * 4 * sizeof(double), st));
+    TDL_KERNEL("area_pyramid", launch_area_pyramid(a->image, a->B, a->H, a->W, J, a->h, a->w, st));
+    TDL_KERNEL("edge_smooth_fwd", launch_smooth_fwd(sm, st));
+    TDL_KERNEL("edge_finalize", launch_edge_finalize(sm.lv[0].acc, 4, a->B, a->first_coef, a->second_coef, a->h, a->w, a->loss, st));
     return TDL_OK;
 }
 
@@ -294,7 +376,8 @@ int tdl_edge_smooth_bwd(const tdl_edge_args* a, tdl_stream_t stream) {
     float* J;
     const int rc = check_edge(a, true, &sm, &J);
     if (rc != TDL_OK) return rc;
-    TDL_CUDA(launch_smooth_bwd(sm, static_cast<cudaStream_t>(stream)));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDL_KERNEL("edge_smooth_bwd", launch_smooth_bwd(sm, st));
     return TDL_OK;
 }
 

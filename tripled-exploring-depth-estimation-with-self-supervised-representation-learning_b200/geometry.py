@@ -51,13 +51,20 @@ def transformation_from_parameters(axisangle, translation, invert=False):
     return torch.matmul(R, T) if invert else torch.matmul(T, R)
 
 
-def half_res_intrinsics(K: torch.Tensor):
-    """K with rows 0,1 halved and its pseudo-inverse, batched (the reference
-    loops torch.pinverse per sample; torch.linalg.pinv batches the same SVD)."""
+def half_res_intrinsics(K: torch.Tensor, inv_K: torch.Tensor | None = None):
+    """K with rows 0,1 halved, and its inverse (mono/model/mono_fm/net.py:185-191).
+
+    The reference runs a per-sample ``torch.pinverse`` (an SVD per image, per frame, per scale).
+    K_half = D @ K with D = diag(1/2, 1/2, 1, 1), so inv(K_half) = inv(K) @ diag(2, 2, 1, 1): when the
+    dataset's ``inv_K`` (= pinv(K), mono_dataset.py:176) is at hand the result is obtained by doubling its
+    first two columns -- exact in fp32 -- instead of a decomposition; otherwise one batched pinv is used."""
     Kh = K.clone()
-    Kh[:, 0, :] /= 2
-    Kh[:, 1, :] /= 2
-    return Kh, torch.linalg.pinv(Kh)
+    Kh[:, 0:2, :] *= 0.5
+    if inv_K is None:
+        return Kh, torch.linalg.pinv(Kh)
+    inv = inv_K.clone()
+    inv[:, :, 0:2] *= 2.0
+    return Kh, inv
 
 
 def projection_matrix(K: torch.Tensor, T: torch.Tensor) -> torch.Tensor:

@@ -33,6 +33,29 @@ from .ops import (EdgeAwareSmoothness, EdgeConfig, FeatConfig, FeatureMetricLoss
                   PhotometricSmoothLoss)
 
 
+class LossDict(dict):
+    """The reference's ``loss_dict`` (same keys, 0-dim tensors) plus ``total()``: the sum of all entries
+    -- what ``batch_processor`` computes (mono/apis/trainer.py:39-48) -- evaluated from the raw kernel
+    outputs with two tiny kernels instead of one add (and one autograd node) per entry."""
+
+    def __init__(self):
+        super().__init__()
+        self._parts = []          # (tensor, multiplicity)
+
+    def add_part(self, tensor, mult=1):
+        self._parts.append((tensor, mult))
+
+    def total(self):
+        if not self._parts:
+            return sum(self.values())
+        out = None
+        for t, m in self._parts:
+            v = t.sum() if t.dim() else t
+            v = v * m if m != 1 else v
+            out = v if out is None else out + v
+        return out
+
+
 def _opt_get(opt, name, default=None):
     if hasattr(opt, "get"):
         return opt.get(name, default)
@@ -114,7 +137,7 @@ class ViewSynthesisLossMixin:
     def _feature_metric(self, inputs, outputs, tgt_f, src_fs: Dict, coef: float, materialize=None):
         opt = self.opt
         frames = self._src_frames()
-        Kh, invKh = half_res_intrinsics(inputs["K"])
+        Kh, invKh = half_res_intrinsics(inputs["K"], inputs.get("inv_K"))
         P = self._stack_P(inputs, outputs, Kh)
         cfg = FeatConfig(n_src=len(frames), min_depth=float(opt.min_depth), max_depth=float(opt.max_depth),
                          align_corners=self.grid_sample_align_corners, coef=float(coef),
@@ -143,7 +166,8 @@ class ViewSynthesisLossMixin:
         """mono/model/mono_baseline/net.py:51-100."""
         scales = list(self.opt.scales)
         losses = self._photometric(inputs, outputs, scales, noise)
-        loss_dict = {}
+        loss_dict = LossDict()
+        loss_dict.add_part(losses)
         for i, s in enumerate(scales):
             loss_dict[("min_reconstruct_loss", s)] = losses[i]
             loss_dict[("smooth_loss", s)] = losses[len(scales) + i]
@@ -161,7 +185,9 @@ class ViewSynthesisLossMixin:
         if tgt_f is None:
             tgt_f = self._extract(inputs[("color", 0, 0)])
         per, idx = self._feature_metric(inputs, outputs, tgt_f, src_fs, opt.perception_weight / len(scales))
-        ordered = {}
+        ordered = LossDict()
+        ordered._parts = list(loss_dict._parts)
+        ordered.add_part(per, len(scales))
         for s in scales:
             ordered[("min_reconstruct_loss", s)] = loss_dict[("min_reconstruct_loss", s)]
             ordered[("min_perceptional_loss", s)] = per
@@ -175,19 +201,23 @@ class ViewSynthesisLossMixin:
         feature-metric term on features[0] (:58-70) and the per-scale photometric / smoothness terms
         (:96-131), plus get_feature_regularization_loss on the five feature levels (:53-56)."""
         opt = self.opt
-        loss_dict = {}
+        loss_dict = LossDict()
         target = inputs[("color", 0, 0)]
         if features is not None:
             for i in range(5):
                 loss_dict[("feature_regularization_loss", i)] = self.get_feature_regularization_loss(
                     features[i], target) / (2 ** i) / 5
+                loss_dict.add_part(loss_dict[("feature_regularization_loss", i)])
             if src_fs is None:
                 src_fs = {f: self._extract(inputs[("color", f, 0)]) for f in self._src_frames()}
             per, idx = self._feature_metric(inputs, outputs, features[0], src_fs, opt.perception_weight)
             loss_dict["min_perceptional_loss"] = per
+            loss_dict.add_part(per)
             if idx is not None:
                 outputs["min_index"] = idx
-        loss_dict.update(self.compute_losses_baseline(inputs, outputs, noise))
+        base = self.compute_losses_baseline(inputs, outputs, noise)
+        loss_dict.update(base)
+        loss_dict._parts += base._parts
         return loss_dict
 
     def get_feature_regularization_loss(self, feature, img):
