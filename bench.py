@@ -208,6 +208,24 @@ class DeviceStep:
         return sum(v.numel() * v.element_size() for v in self.host.values())
 
 
+def rank_seed(rank):
+    """Batch sharding: every rank draws its own synthetic batch (weak scaling, no data-path collective)."""
+    return 1234 + rank
+
+
+def max_over_ranks(ms, device, dist_on):
+    """Multi-GPU numbers are the MAX over ranks of the device-timed region."""
+    if not dist_on:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t)
+
+
+def whole_job_images_per_s(world, batch, steps, ms):
+    return world * batch * steps / (ms * 1e-3)
+
+
 def timed_region(fn, steps, device, dist_on):
     if dist_on:
         torch.distributed.barrier()
@@ -220,12 +238,7 @@ def timed_region(fn, steps, device, dist_on):
     torch.cuda.synchronize(device)
     if dist_on:
         torch.distributed.barrier()
-    ms = a.elapsed_time(b)
-    if dist_on:
-        t = torch.tensor([ms], device=device)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = float(t)
-    return ms
+    return max_over_ranks(a.elapsed_time(b), device, dist_on)
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -312,7 +325,7 @@ def main():
     tdl._lib.lib()                                   # fail loudly if libtdl.so is missing
 
     B, H, W = args.batch, args.height, args.width
-    host = make_host_workload(B, H, W, 1234 + rank)
+    host = make_host_workload(B, H, W, rank_seed(rank))
     side = torch.cuda.Stream(device)
     torch.cuda.set_stream(side)              # every launch, copy and timing event below is on this stream
     step = DeviceStep(host, B, H, W, device, trainable)
@@ -337,7 +350,7 @@ def main():
         step.replay()
     ms = timed_region(step.replay, args.steps, device, dist_on)
     clocks = sampler.stop() if rank == 0 else None
-    value = world * B * args.steps / (ms * 1e-3)
+    value = whole_job_images_per_s(world, B, args.steps, ms)
 
     # ---- e2e: host buffers -> H2D -> step -> D2H of the loss scalars, every step, synchronised like the
     #      reference's per-iteration .item() (mono/apis/trainer.py:52-54)
@@ -351,7 +364,7 @@ def main():
         e2e_step()
     e2e_steps = min(args.steps, 20)
     ms_e2e = timed_region(e2e_step, e2e_steps, device, dist_on)
-    e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
+    e2e_value = whole_job_images_per_s(world, B, e2e_steps, ms_e2e)
 
     if rank != 0:
         if dist_on:
@@ -381,8 +394,14 @@ def main():
     dom = max((k for k in kernels if "alg_bytes" in kernels[k]), key=lambda k: kernels[k]["us_per_step"])
     achieved = kernels[dom]["gbs"]
     total_alg = sum(alg.values())
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed
+        tj = json.load(open(tpath))  # `ncu --set full` capture of this same default workload
+        if tj.get("workload") == [B, H, W, S, FEAT_C] and dom in tj.get("kernels", {}):
+            traffic = tj["kernels"][dom]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg[dom],
                 "whole_step": {"alg_bytes": total_alg, "gbs": round(total_alg / (ms / args.steps * 1e-3) / 1e9, 1),
                                "frac": round(total_alg / (ms / args.steps * 1e-3) / 1e9 / peak, 4)},
