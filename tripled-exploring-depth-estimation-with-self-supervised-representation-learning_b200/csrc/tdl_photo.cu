@@ -336,9 +336,12 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
     const float* db = p.disp[s] + (size_t)b * h * w;
     const unsigned char* am = p.argmin + ((size_t)s * p.B + b) * HW;
 
-    // ---- phase 1: target, argmin mask and re-computed warps over the tile with halo 2
+    // ---- phase 1: target, argmin mask and the warped sources over the tile with halo 2.  When the forward
+    //      materialised outputs[("color",f,s)] they are re-read (coalesced, bit-identical to what the forward
+    //      scored); otherwise the warp is recomputed.
     {
         const float* tb = p.target + (size_t)b * 3 * HW;
+        const bool have_warped = p.warped[s][0] != nullptr;
         for (int i = tid; i < QPLANE; i += kNT) {
             const int r = i / QW, c = i - r * QW;
             const int ry = ty0 - 2 + r, rx = tx0 - 2 + c;
@@ -348,15 +351,25 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
             s_mask[i] = inside ? am[o] : (unsigned char)255;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) s_tgt[ch * QPLANE + i] = __ldg(tb + ch * HW + o);
-            const UpTap ut = up_tap(py, px, p.sy[s], p.sx[s], h, w);
-            const Geo g = backproject(up_value(db, w, ut), dp, s_iK, px, py);
+            if (have_warped) {
 #pragma unroll
-            for (int f = 0; f < S; ++f) {
-                const Proj pr = project<false>(g, s_cam + f * 12, H, W, p.align_corners);
-                const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
-                const float* sb = p.src[f] + (size_t)b * 3 * HW;
+                for (int f = 0; f < S; ++f) {
+                    const float* wb = p.warped[s][f] + (size_t)b * 3 * HW + o;
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) s_wrp[(f * 3 + ch) * QPLANE + i] = bilin_sample(sb + ch * HW, W, bt);
+                    for (int ch = 0; ch < 3; ++ch) s_wrp[(f * 3 + ch) * QPLANE + i] = __ldg(wb + ch * HW);
+                }
+            } else {
+                const UpTap ut = up_tap(py, px, p.sy[s], p.sx[s], h, w);
+                const Geo g = backproject(up_value(db, w, ut), dp, s_iK, px, py);
+#pragma unroll
+                for (int f = 0; f < S; ++f) {
+                    const Proj pr = project<false>(g, s_cam + f * 12, H, W, p.align_corners);
+                    const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
+                    const float* sb = p.src[f] + (size_t)b * 3 * HW;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+                        s_wrp[(f * 3 + ch) * QPLANE + i] = bilin_sample(sb + ch * HW, W, bt);
+                }
             }
         }
     }
@@ -425,7 +438,57 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
         }
         __syncthreads();
 
-        // ---- phase 3: gather the window adjoint, chain through sampling and projection
+        // ---- phase 3: gather the window adjoint (3x3 box sums of the coefficient planes, shared along the
+        //      thread's vertical strip), then chain through sampling and projection for the pixels that
+        //      actually receive gradient from this source frame.
+        float G[3][kR];
+        {
+            const int qc = lane + 2;                                  // Q column of this thread's pixels
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float box[3][kR];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float* pl = s_coef + (ch * 3 + k) * QPLANE + (r0 + 1) * QW + qc;
+                    float hsum[kR + 2];
+#pragma unroll
+                    for (int j = 0; j < kR + 2; ++j) hsum[j] = pl[j * QW - 1] + pl[j * QW] + pl[j * QW + 1];
+#pragma unroll
+                    for (int i = 0; i < kR; ++i) box[k][i] = hsum[i] + hsum[i + 1] + hsum[i + 2];
+                }
+#pragma unroll
+                for (int i = 0; i < kR; ++i) {
+                    const int gy = ty0 + r0 + i;
+                    const int q = (r0 + i + 2) * QW + qc;
+                    // reflect padding: the border windows see their inner neighbour twice (multiplicity 2, 4 in
+                    // the corners) -- add the extra copies for the pixels next to the image border
+                    const bool bx0 = gx == 1, bx1 = gx == W - 2, by0 = gy == 1, by1 = gy == H - 2;
+                    if (bx0 || bx1 || by0 || by1) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const float* c = s_coef + (ch * 3 + k) * QPLANE + q;
+                            float e = 0.f;
+                            if (bx0) e += c[-QW - 1] + c[-1] + c[QW - 1];
+                            if (bx1) e += c[-QW + 1] + c[1] + c[QW + 1];
+                            if (by0) e += c[-QW - 1] + c[-QW] + c[-QW + 1];
+                            if (by1) e += c[QW - 1] + c[QW] + c[QW + 1];
+                            if (bx0 && by0) e += c[-QW - 1];
+                            if (bx1 && by0) e += c[-QW + 1];
+                            if (bx0 && by1) e += c[QW - 1];
+                            if (bx1 && by1) e += c[QW + 1];
+                            box[k][i] += e;
+                        }
+                    }
+                    const float xv = s_wrp[(f * 3 + ch) * QPLANE + q], yv = s_tgt[ch * QPLANE + q];
+                    float g = box[0][i] + 2.f * xv * box[1][i] + yv * box[2][i];
+                    if (s_mask[q] == chan) {
+                        const float df = xv - yv;
+                        g += g_l1 * df * rsqrtf(df * df + kL1Eps2);
+                    }
+                    G[ch][i] = g;
+                }
+            }
+        }
         float aP[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) aP[k] = 0.f;
@@ -433,46 +496,19 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
 #pragma unroll
         for (int i = 0; i < kR; ++i) {
             const int gy = ty0 + r0 + i;
-            if (gx < W && gy < H) {
-                const int q = (r0 + i + 2) * QW + lane + 2;
-                // reflect-padding multiplicity of window centre p for pixel q (1-D each)
-                float mxw[3], myw[3];
-#pragma unroll
-                for (int d = -1; d <= 1; ++d) {
-                    const int pxx = gx + d, pyy = gy + d;
-                    mxw[d + 1] = 1.f + ((pxx == 0 && gx == 1) ? 1.f : 0.f) + ((pxx == W - 1 && gx == W - 2) ? 1.f : 0.f);
-                    myw[d + 1] = 1.f + ((pyy == 0 && gy == 1) ? 1.f : 0.f) + ((pyy == H - 1 && gy == H - 2) ? 1.f : 0.f);
-                }
+            if (gx < W && gy < H && (G[0][i] != 0.f || G[1][i] != 0.f || G[2][i] != 0.f)) {
                 const UpTap ut{s_ty0[r0 + i], s_ty1[r0 + i], s_tx0[lane], s_tx1[lane], s_tly[r0 + i], s_tlx[lane]};
                 const Geo g = backproject(up_value(db, w, ut), dp, s_iK, gx, gy);
                 const Proj pr = project<true>(g, Pf, H, W, p.align_corners);
                 const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
                 const float* sb = p.src[f] + (size_t)b * 3 * HW;
-                const bool sel = s_mask[q] == chan;
                 float gix = 0.f, giy = 0.f;
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    float sA = 0.f, sB = 0.f, sC = 0.f;
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            const float m = mxw[dx + 1] * myw[dy + 1];
-                            const int qq = q + dy * QW + dx;
-                            sA += m * s_coef[(ch * 3 + 0) * QPLANE + qq];
-                            sB += m * s_coef[(ch * 3 + 1) * QPLANE + qq];
-                            sC += m * s_coef[(ch * 3 + 2) * QPLANE + qq];
-                        }
-                    const float xv = s_wrp[(f * 3 + ch) * QPLANE + q], yv = s_tgt[ch * QPLANE + q];
-                    float G = sA + 2.f * xv * sB + yv * sC;
-                    if (sel) {
-                        const float df = xv - yv;
-                        G += g_l1 * df / sqrtf(df * df + kL1Eps2);
-                    }
                     float dix, diy;
                     bilin_sample_grad(sb + ch * HW, W, bt, dix, diy);
-                    gix += G * dix;
-                    giy += G * diy;
+                    gix += G[ch][i] * dix;
+                    giy += G[ch][i] * diy;
                 }
                 const float gu = gix * pr.mx, gv = giy * pr.my;
                 const float rz = 1.f / pr.z;

@@ -118,7 +118,9 @@ class PhotometricSmoothLoss(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(L.tdl_photo_fwd(C.byref(a), _stream()), "tdl_photo_fwd")
         ctx.cfg = cfg
-        ctx.save_for_backward(target, P, invK, ws, *srcs, *disps)
+        ctx.n_warped = len(warped)
+        # the backward re-reads the materialised warps instead of re-projecting the tile halo
+        ctx.save_for_backward(target, P, invK, ws, *srcs, *disps, *warped)
         ctx.mark_non_differentiable(*warped, *min_index)
         return (losses, *warped, *min_index)
 
@@ -130,9 +132,12 @@ class PhotometricSmoothLoss(torch.autograd.Function):
         target, P, invK, ws = ctx.saved_tensors[:4]
         srcs = ctx.saved_tensors[4:4 + S]
         disps = ctx.saved_tensors[4 + S:4 + S + n]
+        warped = ctx.saved_tensors[4 + S + n:4 + S + n + ctx.n_warped]
         B, _, H, W = target.shape
         a = PhotoArgs()
         a.B, a.H, a.W, a.S, a.nscales = B, H, W, S, n
+        for i, t in enumerate(warped):
+            a.warped[i // S][i % S] = t.data_ptr()
         d_disps = []
         for s, d in enumerate(disps):
             a.disp_h[s], a.disp_w[s] = d.shape[2], d.shape[3]
