@@ -43,16 +43,49 @@ __global__ void __launch_bounds__(kFeatNT) feat_fwd_kernel(const FeatDev p) {
         float acc[S];
 #pragma unroll
         for (int f = 0; f < S; ++f) acc[f] = 0.f;
-        const float* tb = p.tgt + (size_t)b * C * hw + pix;
-#pragma unroll 2
-        for (int c = 0; c < C; ++c) {
-            const float t = __ldg(tb + (size_t)c * hw);
+        // corner offsets with clamped east / south taps: a clamped tap always has weight 0 (ix == w-1 or
+        // iy == h-1 after border clipping), so loading it unconditionally adds exactly 0 -- and every load
+        // of a channel batch can be issued before the first use (memory-level parallelism).
+        int o00[S], o01[S], o10[S], o11[S];
 #pragma unroll
-            for (int f = 0; f < S; ++f) {
-                const float v = bilin_sample(p.src[f] + ((size_t)b * C + c) * hw, w, bt[f]);
-                if (p.warped[f]) p.warped[f][((size_t)b * C + c) * hw + pix] = v;
-                const float df = __fsub_rn(v, t);                                  // robust_l1(tgt_f, src_f)
-                acc[f] += __fsqrt_rn(__fadd_rn(__fmul_rn(df, df), kL1Eps2));
+        for (int f = 0; f < S; ++f) {
+            const int x1 = min(bt[f].x0 + 1, w - 1), y1 = min(bt[f].y0 + 1, h - 1);
+            o00[f] = bt[f].y0 * w + bt[f].x0;
+            o01[f] = bt[f].y0 * w + x1;
+            o10[f] = y1 * w + bt[f].x0;
+            o11[f] = y1 * w + x1;
+        }
+        constexpr int CB = (S <= 2) ? 8 : 4;                       // channels per batch
+        const float* tb = p.tgt + (size_t)b * C * hw + pix;
+        for (int c0 = 0; c0 < C; c0 += CB) {
+            float t[CB], v[S][CB][4];
+#pragma unroll
+            for (int j = 0; j < CB; ++j) {
+                const int c = min(c0 + j, C - 1);
+                t[j] = __ldg(tb + (size_t)c * hw);
+#pragma unroll
+                for (int f = 0; f < S; ++f) {
+                    const float* pl = p.src[f] + ((size_t)b * C + c) * hw;
+                    v[f][j][0] = __ldg(pl + o00[f]);
+                    v[f][j][1] = __ldg(pl + o01[f]);
+                    v[f][j][2] = __ldg(pl + o10[f]);
+                    v[f][j][3] = __ldg(pl + o11[f]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < CB; ++j) {
+                if (c0 + j < C) {
+#pragma unroll
+                    for (int f = 0; f < S; ++f) {
+                        float val = v[f][j][0] * bt[f].nw;
+                        val += v[f][j][1] * bt[f].ne;
+                        val += v[f][j][2] * bt[f].sw;
+                        val += v[f][j][3] * bt[f].se;
+                        if (p.warped[f]) p.warped[f][((size_t)b * C + c0 + j) * hw + pix] = val;
+                        const float df = __fsub_rn(val, t[j]);                     // robust_l1(tgt_f, src_f)
+                        acc[f] += __fsqrt_rn(__fadd_rn(__fmul_rn(df, df), kL1Eps2));
+                    }
+                }
             }
         }
         int arg = 0;
@@ -82,6 +115,12 @@ __global__ void feat_finalize_kernel(const double* __restrict__ acc, int B, doub
 }
 
 // Backward: only the arg-min source of each pixel receives gradient (torch.min backward).
+//
+// d_src scatter: a pixel adds g*w to the four corners of its sampling point.  Global reductions (RED) issue
+// at ~1.3 cycles per lane per SM on B200, so 4 atomics x C channels per pixel would bound the kernel.  Along
+// a row the sampling points of neighbouring pixels are (almost always) one source pixel apart, i.e. the
+// north-east / south-east corner of lane i IS the north-west / south-west corner of lane i+1: lane i+1 takes
+// those two contributions over with a warp shuffle and lane i skips its two atomics ("absorbed").
 template <bool kGradFeat>
 __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
     __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
@@ -98,55 +137,93 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
     __syncthreads();
     const int pix = blockIdx.x * kFeatNT + tid;
     const bool active = pix < (int)hw;
-    float aP[12];
+    const int y = active ? pix / w : 0, x = active ? pix - y * w : 0;
+    const int fsel = active ? p.argmin[(size_t)b * hw + pix] : -1;
+    const DepthParams dp{p.min_disp, p.range};
+    const UpTap ut = up_tap(y, x, p.sy, p.sx, p.dh, p.dw);
+    const Geo g = backproject(up_value(p.disp + (size_t)b * p.dh * p.dw, p.dw, ut), dp, s_cam + TDL_MAX_SRC * 12, x, y);
+    const float* Pf = s_cam + max(fsel, 0) * 12;
+    const Proj pr = project<true>(g, Pf, h, w, p.align_corners);
+    const Bilin bt = bilin_taps(pr.ix, pr.iy, h, w);
+    const float up = active ? __ldg(p.dloss) * p.coef / ((float)p.B * (float)h * (float)w) / (float)C : 0.f;
+    const float* sb = p.src[0];
+    float* dsb = kGradFeat ? p.d_src[0] : nullptr;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) aP[k] = 0.f;
-    int fsel = 0;
-    if (active) {
-        const int y = pix / w, x = pix - y * w;
-        fsel = p.argmin[(size_t)b * hw + pix];
-        const DepthParams dp{p.min_disp, p.range};
-        const UpTap ut = up_tap(y, x, p.sy, p.sx, p.dh, p.dw);
-        const Geo g = backproject(up_value(p.disp + (size_t)b * p.dh * p.dw, p.dw, ut), dp,
-                                  s_cam + TDL_MAX_SRC * 12, x, y);
-        const float* Pf = s_cam + fsel * 12;
-        const Proj pr = project<true>(g, Pf, h, w, p.align_corners);
-        const Bilin bt = bilin_taps(pr.ix, pr.iy, h, w);
-        const float up = __ldg(p.dloss) * p.coef / ((float)p.B * (float)h * (float)w) / (float)C;
-        const float* sb = p.src[0];
-#pragma unroll
-        for (int f = 1; f < TDL_MAX_SRC; ++f)
-            if (f == fsel) sb = p.src[f];
-        float* dsb = nullptr;
-        if (kGradFeat) {
-            dsb = p.d_src[0];
-#pragma unroll
-            for (int f = 1; f < TDL_MAX_SRC; ++f)
-                if (f == fsel) dsb = p.d_src[f];
+    for (int f = 1; f < TDL_MAX_SRC; ++f)
+        if (f == fsel) {
+            sb = p.src[f];
+            if (kGradFeat) dsb = p.d_src[f];
         }
-        const float* tb = p.tgt + (size_t)b * C * hw + pix;
-        float gix = 0.f, giy = 0.f;
-#pragma unroll 2
-        for (int c = 0; c < C; ++c) {
-            const size_t plane = ((size_t)b * C + c) * hw;
-            const float t = __ldg(tb + (size_t)c * hw);
-            float dix, diy;
-            const float v = bilin_sample_grad(sb + plane, w, bt, dix, diy);
-            const float df = v - t;
-            const float gvv = up * df / sqrtf(df * df + kL1Eps2);      // d loss / d warped value
-            gix += gvv * dix;
-            giy += gvv * diy;
-            if (kGradFeat) {
-                if (p.d_tgt) p.d_tgt[plane + pix] = -gvv;
-                if (dsb) {
-                    float* q = dsb + plane + (size_t)bt.y0 * w + bt.x0;
-                    atomicAdd(q, gvv * bt.nw);
-                    if (bt.vx) atomicAdd(q + 1, gvv * bt.ne);
-                    if (bt.vy) atomicAdd(q + w, gvv * bt.sw);
-                    if (bt.vx && bt.vy) atomicAdd(q + w + 1, gvv * bt.se);
+    const int x1 = min(bt.x0 + 1, w - 1), y1 = min(bt.y0 + 1, h - 1);
+    const int o00 = bt.y0 * w + bt.x0, o01 = bt.y0 * w + x1, o10 = y1 * w + bt.x0, o11 = y1 * w + x1;
+
+    // absorption pattern (channel independent)
+    bool absorbed = false, absorbs = false;          // my east taps are taken over by lane+1 / I take lane-1's
+    if (kGradFeat && dsb) {
+        const int nx0 = __shfl_down_sync(0xffffffffu, bt.x0, 1), ny0 = __shfl_down_sync(0xffffffffu, bt.y0, 1);
+        const int nf = __shfl_down_sync(0xffffffffu, fsel, 1);
+        absorbed = active && lane < 31 && nf == fsel && ny0 == bt.y0 && nx0 == bt.x0 + 1 && bt.vx;
+        absorbs = __shfl_up_sync(0xffffffffu, (int)absorbed, 1) != 0 && lane > 0;
+    }
+
+    constexpr int CB = 8;
+    const float* tb = p.tgt + (size_t)b * C * hw + pix;
+    float gix = 0.f, giy = 0.f;
+    for (int c0 = 0; c0 < C; c0 += CB) {
+        float t[CB], v[CB][4];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+            const int c = min(c0 + j, C - 1);
+            const float* pl = sb + ((size_t)b * C + c) * hw;
+            t[j] = active ? __ldg(tb + (size_t)c * hw) : 0.f;
+            v[j][0] = active ? __ldg(pl + o00) : 0.f;
+            v[j][1] = active ? __ldg(pl + o01) : 0.f;
+            v[j][2] = active ? __ldg(pl + o10) : 0.f;
+            v[j][3] = active ? __ldg(pl + o11) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+            if (c0 + j < C) {                                             // uniform across the warp
+                const size_t plane = ((size_t)b * C + c0 + j) * hw;
+                // zero weight <=> clamped tap: same arithmetic as bilin_sample_grad with the tap skipped
+                const float v00 = v[j][0], v01 = bt.vx ? v[j][1] : 0.f, v10 = bt.vy ? v[j][2] : 0.f;
+                const float v11 = (bt.vx && bt.vy) ? v[j][3] : 0.f;
+                const float val = v00 * bt.nw + v01 * bt.ne + v10 * bt.sw + v11 * bt.se;
+                const float dix = -v00 * bt.ey + v01 * bt.ey - v10 * bt.ay + v11 * bt.ay;
+                const float diy = -v00 * bt.ex - v01 * bt.ax + v10 * bt.ex + v11 * bt.ax;
+                const float df = val - t[j];
+                const float gvv = up * df * rsqrtf(df * df + kL1Eps2);      // d loss / d warped value
+                gix += gvv * dix;
+                giy += gvv * diy;
+                if (kGradFeat) {
+                    if (p.d_tgt && active) p.d_tgt[plane + pix] = -gvv;
+                    if (dsb) {
+                        float top = gvv * bt.nw, bot = gvv * bt.sw;
+                        const float e_top = gvv * bt.ne, e_bot = gvv * bt.se;
+                        const float in_top = __shfl_up_sync(0xffffffffu, e_top, 1);
+                        const float in_bot = __shfl_up_sync(0xffffffffu, e_bot, 1);
+                        if (absorbs) {
+                            top += in_top;
+                            bot += in_bot;
+                        }
+                        if (active) {
+                            float* q = dsb + plane;
+                            atomicAdd(q + o00, top);
+                            if (bt.vy) atomicAdd(q + o10, bot);
+                            if (!absorbed && bt.vx) {
+                                atomicAdd(q + o01, e_top);
+                                if (bt.vy) atomicAdd(q + o11, e_bot);
+                            }
+                        }
+                    }
                 }
             }
         }
+    }
+    float aP[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) aP[k] = 0.f;
+    if (active) {
         const float gu = gix * pr.mx, gv = giy * pr.my;
         const float rz = 1.f / pr.z;
         const float gp0 = gu * rz, gp1 = gv * rz, gp2 = -(gu * pr.u + gv * pr.v) * rz;
