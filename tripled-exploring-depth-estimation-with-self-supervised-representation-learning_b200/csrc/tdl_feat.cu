@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
     for (int k = 0; k < 12; ++k) aP[k] = 0.f;
     if (active) {
         const float gu = gix * pr.mx, gv = giy * pr.my;
-        const float rz = 1.f / pr.z;
+        const float rz = __frcp_rn(pr.z);
         const float gp0 = gu * rz, gp1 = gv * rz, gp2 = -(gu * pr.u + gv * pr.v) * rz;
         aP[0] = gp0 * g.X0; aP[1] = gp0 * g.X1; aP[2] = gp0 * g.X2; aP[3] = gp0;
         aP[4] = gp1 * g.X0; aP[5] = gp1 * g.X1; aP[6] = gp1 * g.X2; aP[7] = gp1;

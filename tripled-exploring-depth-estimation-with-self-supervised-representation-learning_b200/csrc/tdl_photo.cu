@@ -74,7 +74,7 @@ TDL_DEV float ssim_value(float mu_x, float mu_y, float sg_x, float sg_y, float s
                               __fadd_rn(__fmul_rn(2.f, sg_xy), kSsimC2));                  // layers.py:104
     const float d = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(mu_x, mu_x), __fmul_rn(mu_y, mu_y)), kSsimC1),
                               __fadd_rn(__fadd_rn(sg_x, sg_y), kSsimC2));                  // layers.py:105
-    const float v = __fdiv_rn(__fsub_rn(1.f, __fdiv_rn(n, d)), 2.f);                       // layers.py:106
+    const float v = __fmul_rn(__fsub_rn(1.f, div_rn(n, d)), 0.5f);                         // layers.py:106
     return fminf(fmaxf(v, 0.f), 1.f);
 }
 
@@ -119,7 +119,7 @@ TDL_DEV void strip_reprojection(const float* __restrict__ pred3, const float* __
         strip_ssim_l1<PITCH>(pred3 + ch * plane, tgt3 + ch * plane, r, c, mu_y[ch], sg_y[ch], sa, la);
 #pragma unroll
     for (int i = 0; i < kR; ++i)
-        rho[i] = __fadd_rn(__fmul_rn(0.85f, __fdiv_rn(sa[i], 3.f)), __fmul_rn(0.15f, __fdiv_rn(la[i], 3.f)));
+        rho[i] = __fadd_rn(__fmul_rn(0.85f, div3(sa[i])), __fmul_rn(0.15f, div3(la[i])));
 }
 
 TDL_DEV float automask_noise(const PhotoDev& p, int s, int f, int b, size_t pix, size_t HW) {
@@ -419,9 +419,9 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
                     const float d1 = __fadd_rn(__fadd_rn(__fmul_rn(mu_x, mu_x), __fmul_rn(mu_y, mu_y)), kSsimC1);
                     const float d2 = __fadd_rn(__fadd_rn(sg_x, sg_y), kSsimC2);
                     const float n = __fmul_rn(n1, n2), d = __fmul_rn(d1, d2);
-                    const float v = __fdiv_rn(__fsub_rn(1.f, __fdiv_rn(n, d)), 2.f);   // identical to the forward
+                    const float v = __fmul_rn(__fsub_rn(1.f, div_rn(n, d)), 0.5f);     // identical to the forward
                     if (v >= 0.f && v <= 1.f) {                           // clamp passes gradient inside [0,1]
-                        const float rd = 1.f / d;
+                        const float rd = __frcp_rn(d);
                         const float gmu = (-mu_y * (n2 - n1) + (n * rd) * mu_x * (d2 - d1)) * rd;
                         const float ga = n * d1 * 0.5f * rd * rd;
                         const float gc = -n1 * rd;
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
                     giy += G[ch][i] * diy;
                 }
                 const float gu = gix * pr.mx, gv = giy * pr.my;
-                const float rz = 1.f / pr.z;
+                const float rz = __frcp_rn(pr.z);
                 const float gp0 = gu * rz, gp1 = gv * rz, gp2 = -(gu * pr.u + gv * pr.v) * rz;
                 aP[0] += gp0 * g.X0; aP[1] += gp0 * g.X1; aP[2] += gp0 * g.X2; aP[3] += gp0;
                 aP[4] += gp1 * g.X0; aP[5] += gp1 * g.X1; aP[6] += gp1 * g.X2; aP[7] += gp1;

@@ -83,7 +83,7 @@ TDL_DEV Stencil6 edge_weights(const float* __restrict__ Jb, int j, int i, int h,
     const bool x1 = i + 1 < w, x2 = i + 2 < w, y1 = j + 1 < h, y2 = j + 2 < h;
     const bool ok[6] = {x1, y1, x2, x1 && y1, x1 && y1, y2};
 #pragma unroll
-    for (int k = 0; k < 6; ++k) m.v[k] = ok[k] ? expf(-alpha * __fdiv_rn(m.v[k], 3.f)) : 0.f;
+    for (int k = 0; k < 6; ++k) m.v[k] = ok[k] ? expf(-alpha * div3(m.v[k])) : 0.f;
     return m;
 }
 
