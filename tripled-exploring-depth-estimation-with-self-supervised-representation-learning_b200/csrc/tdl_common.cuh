@@ -189,13 +189,16 @@ TDL_DEV Bilin bilin_taps(float ix, float iy, int H, int W) {
     return t;
 }
 
-// one channel plane; returns the interpolated value
+// one channel plane; returns the interpolated value.  The east / south taps are loaded from a clamped
+// index: a clamped tap always has weight exactly 0 (ix == W-1 or iy == H-1 after border clipping), so it
+// adds 0 like ATen's skipped out-of-range tap, without predicated loads or branches.
 TDL_DEV float bilin_sample(const float* __restrict__ plane, int W, const Bilin& t) {
     const float* p = plane + (size_t)t.y0 * W + t.x0;
+    const int dx = t.vx ? 1 : 0, dy = t.vy ? W : 0;
     float acc = __ldg(p) * t.nw;
-    if (t.vx) acc += __ldg(p + 1) * t.ne;
-    if (t.vy) acc += __ldg(p + W) * t.sw;
-    if (t.vx && t.vy) acc += __ldg(p + W + 1) * t.se;
+    acc += __ldg(p + dx) * t.ne;
+    acc += __ldg(p + dy) * t.sw;
+    acc += __ldg(p + dy + dx) * t.se;
     return acc;
 }
 

@@ -36,36 +36,36 @@ static_assert(kTH == (kNT / 32) * kR, "tile / thread mapping");
 // nn.AvgPool2d(3,1) of ATen (CPU and CUDA alike) accumulates the window in row-major order and
 // divides by 9; the same order is used here so that, for identical inputs, the statistics -- and with
 // them the rounding noise that torch.clamp(.., 0, 1) rectifies when SSIM ~ 0 -- are bit-identical.
-TDL_DEV float sum9(const float v[kR + 2][3], int i) {
-    float a = v[i][0];
-    a = __fadd_rn(a, v[i][1]);
-    a = __fadd_rn(a, v[i][2]);
-    a = __fadd_rn(a, v[i + 1][0]);
-    a = __fadd_rn(a, v[i + 1][1]);
-    a = __fadd_rn(a, v[i + 1][2]);
-    a = __fadd_rn(a, v[i + 2][0]);
-    a = __fadd_rn(a, v[i + 2][1]);
-    a = __fadd_rn(a, v[i + 2][2]);
-    return a;
+// The strip is streamed row by row: row j is the first row of window j, the second of window j-1 and the
+// third of window j-2, so each window still sees its nine values in row-major order while only three
+// windows are in flight (keeps the register footprint small).
+TDL_DEV void acc_row(float& a, bool first, float v0, float v1, float v2) {
+    a = first ? v0 : __fadd_rn(a, v0);
+    a = __fadd_rn(a, v1);
+    a = __fadd_rn(a, v2);
 }
 
 template <int PITCH>
 TDL_DEV void strip_target_stats(const float* __restrict__ ys, int r, int c, float mu_y[kR], float sg_y[kR]) {
-    float y[kR + 2][3], yy[kR + 2][3];
+    float ay[kR], ayy[kR];
 #pragma unroll
     for (int j = 0; j < kR + 2; ++j) {
         const float* yr = ys + (r + j) * PITCH + c;
+        const float y0 = yr[0], y1 = yr[1], y2 = yr[2];
+        const float q0 = __fmul_rn(y0, y0), q1 = __fmul_rn(y1, y1), q2 = __fmul_rn(y2, y2);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            y[j][k] = yr[k];
-            yy[j][k] = __fmul_rn(yr[k], yr[k]);
+        for (int i = 0; i < kR; ++i) {
+            if (i <= j && j <= i + 2) {
+                acc_row(ay[i], j == i, y0, y1, y2);
+                acc_row(ayy[i], j == i, q0, q1, q2);
+            }
         }
-    }
-#pragma unroll
-    for (int i = 0; i < kR; ++i) {
-        const float m = div9(sum9(y, i));
-        mu_y[i] = m;
-        sg_y[i] = __fsub_rn(div9(sum9(yy, i)), __fmul_rn(m, m));                       // layers.py:102
+        if (j >= 2) {
+            const int i = j - 2;
+            const float m = div9(ay[i]);
+            mu_y[i] = m;
+            sg_y[i] = __fsub_rn(div9(ayy[i]), __fmul_rn(m, m));                           // layers.py:102
+        }
     }
 }
 
@@ -80,43 +80,51 @@ TDL_DEV float ssim_value(float mu_x, float mu_y, float sg_x, float sg_y, float s
 
 template <int PITCH>
 TDL_DEV void strip_ssim_l1(const float* __restrict__ xs, const float* __restrict__ ys, int r, int c,
-                           const float mu_y[kR], const float sg_y[kR], float ssim_acc[kR], float l1_acc[kR]) {
-    float x[kR + 2][3], xx[kR + 2][3], xy[kR + 2][3];
-    float yc[kR];
+                           const float* __restrict__ mu_y, const float* __restrict__ sg_y, float ssim_acc[kR],
+                           float l1_acc[kR]) {
+    float ax[kR], axx[kR], axy[kR];
 #pragma unroll
     for (int j = 0; j < kR + 2; ++j) {
         const float* xr = xs + (r + j) * PITCH + c;
         const float* yr = ys + (r + j) * PITCH + c;
+        const float x0 = xr[0], x1 = xr[1], x2 = xr[2];
+        const float y0 = yr[0], y1 = yr[1], y2 = yr[2];
+        const float q0 = __fmul_rn(x0, x0), q1 = __fmul_rn(x1, x1), q2 = __fmul_rn(x2, x2);
+        const float p0 = __fmul_rn(x0, y0), p1 = __fmul_rn(x1, y1), p2 = __fmul_rn(x2, y2);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float xv = xr[k], yv = yr[k];
-            x[j][k] = xv;
-            xx[j][k] = __fmul_rn(xv, xv);
-            xy[j][k] = __fmul_rn(xv, yv);
-            if (k == 1 && j >= 1 && j <= kR) yc[j - 1] = yv;
+        for (int i = 0; i < kR; ++i) {
+            if (i <= j && j <= i + 2) {
+                acc_row(ax[i], j == i, x0, x1, x2);
+                acc_row(axx[i], j == i, q0, q1, q2);
+                acc_row(axy[i], j == i, p0, p1, p2);
+            }
         }
-    }
-#pragma unroll
-    for (int i = 0; i < kR; ++i) {
-        const float mu_x = div9(sum9(x, i));
-        const float sg_x = __fsub_rn(div9(sum9(xx, i)), __fmul_rn(mu_x, mu_x));
-        const float sg_xy = __fsub_rn(div9(sum9(xy, i)), __fmul_rn(mu_x, mu_y[i]));
-        ssim_acc[i] += ssim_value(mu_x, mu_y[i], sg_x, sg_y[i], sg_xy);
-        const float df = __fsub_rn(yc[i], x[i + 1][1]);                                    // net.py:57
-        l1_acc[i] += __fsqrt_rn(__fadd_rn(__fmul_rn(df, df), kL1Eps2));
+        if (j >= 1 && j <= kR) {                                                           // centre pixel of window j-1
+            const float df = __fsub_rn(y1, x1);                                            // net.py:57
+            l1_acc[j - 1] += __fsqrt_rn(__fadd_rn(__fmul_rn(df, df), kL1Eps2));
+        }
+        if (j >= 2) {
+            const int i = j - 2;
+            const float mu_x = div9(ax[i]);
+            const float my = mu_y[i * kNT], sy = sg_y[i * kNT];                            // [i][thread] layout
+            const float sg_x = __fsub_rn(div9(axx[i]), __fmul_rn(mu_x, mu_x));
+            const float sg_xy = __fsub_rn(div9(axy[i]), __fmul_rn(mu_x, my));
+            ssim_acc[i] += ssim_value(mu_x, my, sg_x, sy, sg_xy);
+        }
     }
 }
 
 // rho = 0.85 * mean_c SSIM + 0.15 * mean_c L1 for the strip (net.py:63-67)
 template <int PITCH>
 TDL_DEV void strip_reprojection(const float* __restrict__ pred3, const float* __restrict__ tgt3, int plane,
-                                int r, int c, const float mu_y[3][kR], const float sg_y[3][kR], float rho[kR]) {
+                                int r, int c, const float* __restrict__ stats, float rho[kR]) {
     float sa[kR], la[kR];
 #pragma unroll
     for (int i = 0; i < kR; ++i) sa[i] = la[i] = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch)
-        strip_ssim_l1<PITCH>(pred3 + ch * plane, tgt3 + ch * plane, r, c, mu_y[ch], sg_y[ch], sa, la);
+        strip_ssim_l1<PITCH>(pred3 + ch * plane, tgt3 + ch * plane, r, c, stats + (ch * 2) * kR * kNT,
+                             stats + (ch * 2 + 1) * kR * kNT, sa, la);
 #pragma unroll
     for (int i = 0; i < kR; ++i)
         rho[i] = __fadd_rn(__fmul_rn(0.85f, div3(sa[i])), __fmul_rn(0.15f, div3(la[i])));
@@ -194,15 +202,23 @@ __global__ void __launch_bounds__(kNT, 2) photo_fwd_kernel(const PhotoDev p) {
     // ---- per-thread strip: column `lane`, rows wrp*kR .. wrp*kR+kR-1 of the tile
     const int r0 = wrp * kR;
     const int gx = tx0 + lane;
-    float mu_y[3][kR], sg_y[3][kR];
+    float* s_stats = s_buf + S * 3 * PLANE + tid;      // [ch][mu|sigma][i][thread]
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) strip_target_stats<PW>(s_tgt + ch * PLANE, r0, lane, mu_y[ch], sg_y[ch]);
+    for (int ch = 0; ch < 3; ++ch) {
+        float mu_y[kR], sg_y[kR];
+        strip_target_stats<PW>(s_tgt + ch * PLANE, r0, lane, mu_y, sg_y);
+#pragma unroll
+        for (int i = 0; i < kR; ++i) {
+            s_stats[((ch * 2) * kR + i) * kNT] = mu_y[i];
+            s_stats[((ch * 2 + 1) * kR + i) * kNT] = sg_y[i];
+        }
+    }
 
     float rho_id[S][kR];
     if (p.automask) {
 #pragma unroll
         for (int f = 0; f < S; ++f)
-            strip_reprojection<PW>(s_buf + f * 3 * PLANE, s_tgt, PLANE, r0, lane, mu_y, sg_y, rho_id[f]);
+            strip_reprojection<PW>(s_buf + f * 3 * PLANE, s_tgt, PLANE, r0, lane, s_stats, rho_id[f]);
     }
     __syncthreads();
 
@@ -259,7 +275,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_fwd_kernel(const PhotoDev p) {
 #pragma unroll
         for (int f = 0; f < S; ++f) {
             float rho[kR];
-            strip_reprojection<PW>(s_buf + f * 3 * PLANE, s_tgt, PLANE, r0, lane, mu_y, sg_y, rho);
+            strip_reprojection<PW>(s_buf + f * 3 * PLANE, s_tgt, PLANE, r0, lane, s_stats, rho);
 #pragma unroll
             for (int i = 0; i < kR; ++i) {
                 if (arg[i] < 0 || rho[i] < best[i]) {
@@ -569,7 +585,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
 template <int S>
 static cudaError_t launch_fwd_t(const PhotoDev& p, cudaStream_t st) {
     constexpr int PLANE = (kTW + 2) * (kTH + 2);
-    const size_t smem = (size_t)(3 + 3 * S) * PLANE * sizeof(float);
+    const size_t smem = (size_t)(3 + 3 * S) * PLANE * sizeof(float) + (size_t)6 * kR * kNT * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(photo_fwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
