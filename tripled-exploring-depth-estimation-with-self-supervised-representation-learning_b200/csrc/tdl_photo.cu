@@ -327,6 +327,8 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
     unsigned char* s_mask = reinterpret_cast<unsigned char*>(s_coef + 9 * QPLANE);   // [QPLANE]
     __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
     __shared__ float s_dP[TDL_MAX_SRC * 12];
+    __shared__ int s_cnt[TDL_MAX_SRC];
+    __shared__ unsigned short s_list[PH * PW];
     __shared__ int s_tx0[kTW], s_tx1[kTW], s_ty0[kTH], s_ty1[kTH];
     __shared__ float s_tlx[kTW], s_tly[kTH];
 
@@ -342,6 +344,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
         s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
         s_dP[tid] = 0.f;
     }
+    if (tid >= 128 && tid < 128 + TDL_MAX_SRC) s_cnt[tid - 128] = 0;
     if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
     const float* s_iK = s_cam + TDL_MAX_SRC * 12;
     if (tid < kTW) up_index(tx0 + tid, p.sx[s], w, s_tx0[tid], s_tx1[tid], s_tlx[tid]);
@@ -354,27 +357,55 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
 
     // ---- phase 1: target, argmin mask and the warped sources over the tile with halo 2.  When the forward
     //      materialised outputs[("color",f,s)] they are re-read (coalesced, bit-identical to what the forward
-    //      scored); otherwise the warp is recomputed.
+    //      scored); otherwise the warp is recomputed.  All loads of a thread are issued before the first
+    //      shared-memory store (the kernel is latency-bound here: ~10 loads x 5 cells per thread).
     {
         const float* tb = p.target + (size_t)b * 3 * HW;
         const bool have_warped = p.warped[s][0] != nullptr;
-        for (int i = tid; i < QPLANE; i += kNT) {
-            const int r = i / QW, c = i - r * QW;
-            const int ry = ty0 - 2 + r, rx = tx0 - 2 + c;
-            const bool inside = ry >= 0 && ry < H && rx >= 0 && rx < W;
-            const int py = reflect1(ry, H), px = reflect1(rx, W);
-            const size_t o = (size_t)py * W + px;
-            s_mask[i] = inside ? am[o] : (unsigned char)255;
+        constexpr int NIT = (QPLANE + kNT - 1) / kNT;
+        if (have_warped) {
+            float tv[NIT][3], wv[NIT][S][3];
+            unsigned char mv[NIT];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) s_tgt[ch * QPLANE + i] = __ldg(tb + ch * HW + o);
-            if (have_warped) {
+            for (int it = 0; it < NIT; ++it) {
+                const int i = min(tid + it * kNT, QPLANE - 1);
+                const int r = i / QW, c = i - r * QW;
+                const int ry = ty0 - 2 + r, rx = tx0 - 2 + c;
+                const bool inside = ry >= 0 && ry < H && rx >= 0 && rx < W;
+                const size_t o = (size_t)reflect1(ry, H) * W + reflect1(rx, W);
+                mv[it] = inside ? am[o] : (unsigned char)255;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) tv[it][ch] = __ldg(tb + ch * HW + o);
 #pragma unroll
                 for (int f = 0; f < S; ++f) {
                     const float* wb = p.warped[s][f] + (size_t)b * 3 * HW + o;
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) s_wrp[(f * 3 + ch) * QPLANE + i] = __ldg(wb + ch * HW);
+                    for (int ch = 0; ch < 3; ++ch) wv[it][f][ch] = __ldg(wb + ch * HW);
                 }
-            } else {
+            }
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int i = tid + it * kNT;
+                if (i < QPLANE) {
+                    s_mask[i] = mv[it];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) s_tgt[ch * QPLANE + i] = tv[it][ch];
+#pragma unroll
+                    for (int f = 0; f < S; ++f)
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) s_wrp[(f * 3 + ch) * QPLANE + i] = wv[it][f][ch];
+                }
+            }
+        } else {
+            for (int i = tid; i < QPLANE; i += kNT) {
+                const int r = i / QW, c = i - r * QW;
+                const int ry = ty0 - 2 + r, rx = tx0 - 2 + c;
+                const bool inside = ry >= 0 && ry < H && rx >= 0 && rx < W;
+                const int py = reflect1(ry, H), px = reflect1(rx, W);
+                const size_t o = (size_t)py * W + px;
+                s_mask[i] = inside ? am[o] : (unsigned char)255;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) s_tgt[ch * QPLANE + i] = __ldg(tb + ch * HW + o);
                 const UpTap ut = up_tap(py, px, p.sy[s], p.sx[s], h, w);
                 const Geo g = backproject(up_value(db, w, ut), dp, s_iK, px, py);
 #pragma unroll
@@ -397,19 +428,38 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
 #pragma unroll
     for (int i = 0; i < kR; ++i) gd[i] = 0.f;
     const float g_ssim = up * 0.85f / 3.f, g_l1 = up * 0.15f / 3.f;
+    // depth / ray / camera point of this thread's pixels do not depend on the source frame
+    Geo geo[kR];
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+        const UpTap ut{s_ty0[r0 + i], s_ty1[r0 + i], s_tx0[lane], s_tx1[lane], s_tly[r0 + i], s_tlx[lane]};
+        geo[i] = backproject(up_value(db, w, ut), dp, s_iK, gx, ty0 + r0 + i);
+    }
 
 #pragma unroll 1
     for (int f = 0; f < S; ++f) {
         const int chan = (p.automask ? S : 0) + f;
-        // ---- phase 2: SSIM adjoint coefficients of every window centre (tile + halo 1)
+        // ---- phase 2: SSIM adjoint coefficients of every window centre (tile + halo 1).  Only windows whose
+        //      arg-min is this source frame carry gradient: they are compacted into a list first so that the
+        //      heavy statistics run with full warps and an even share per thread; the others just store zeros.
         for (int i = tid; i < PH * PW; i += kNT) {
             const int r = i / PW, c = i - r * PW;
             const int q = (r + 1) * QW + (c + 1);
-            const bool sel = s_mask[q] == chan;
+            if (s_mask[q] == chan) {
+                s_list[atomicAdd(&s_cnt[f], 1)] = (unsigned short)q;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) s_coef[k * QPLANE + q] = 0.f;
+            }
+        }
+        __syncthreads();
+        const int n_sel = s_cnt[f];
+        for (int e = tid; e < n_sel; e += kNT) {
+            const int q = s_list[e];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 float cA = 0.f, cB = 0.f, cC = 0.f;
-                if (sel) {
+                {
                     const float* xs = s_wrp + (f * 3 + ch) * QPLANE + q;
                     const float* ys = s_tgt + ch * QPLANE + q;
                     float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
@@ -509,34 +559,61 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
 #pragma unroll
         for (int k = 0; k < 12; ++k) aP[k] = 0.f;
         const float* Pf = s_cam + f * 12;
+        const float* sbase = p.src[f] + (size_t)b * 3 * HW;
 #pragma unroll
-        for (int i = 0; i < kR; ++i) {
-            const int gy = ty0 + r0 + i;
-            if (gx < W && gy < H && (G[0][i] != 0.f || G[1][i] != 0.f || G[2][i] != 0.f)) {
-                const UpTap ut{s_ty0[r0 + i], s_ty1[r0 + i], s_tx0[lane], s_tx1[lane], s_tly[r0 + i], s_tlx[lane]};
-                const Geo g = backproject(up_value(db, w, ut), dp, s_iK, gx, gy);
-                const Proj pr = project<true>(g, Pf, H, W, p.align_corners);
-                const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
-                const float* sb = p.src[f] + (size_t)b * 3 * HW;
-                float gix = 0.f, giy = 0.f;
+        for (int i0 = 0; i0 < kR; i0 += 2) {
+            bool act[2];
+            Proj pr[2];
+            Bilin bt[2];
+            float v[2][3][4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = i0 + u, gy = ty0 + r0 + i;
+                act[u] = gx < W && gy < H && (G[0][i] != 0.f || G[1][i] != 0.f || G[2][i] != 0.f);
+                pr[u] = project<true>(geo[i], Pf, H, W, p.align_corners);
+                bt[u] = bilin_taps(pr[u].ix, pr[u].iy, H, W);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float* q = sbase + (size_t)bt[u].y0 * W + bt[u].x0;
+                const int dx = bt[u].vx ? 1 : 0, dy = bt[u].vy ? W : 0;
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    float dix, diy;
-                    bilin_sample_grad(sb + ch * HW, W, bt, dix, diy);
-                    gix += G[ch][i] * dix;
-                    giy += G[ch][i] * diy;
+                    v[u][ch][0] = act[u] ? __ldg(q + ch * HW) : 0.f;
+                    v[u][ch][1] = act[u] ? __ldg(q + ch * HW + dx) : 0.f;
+                    v[u][ch][2] = act[u] ? __ldg(q + ch * HW + dy) : 0.f;
+                    v[u][ch][3] = act[u] ? __ldg(q + ch * HW + dy + dx) : 0.f;
                 }
-                const float gu = gix * pr.mx, gv = giy * pr.my;
-                const float rz = __frcp_rn(pr.z);
-                const float gp0 = gu * rz, gp1 = gv * rz, gp2 = -(gu * pr.u + gv * pr.v) * rz;
-                aP[0] += gp0 * g.X0; aP[1] += gp0 * g.X1; aP[2] += gp0 * g.X2; aP[3] += gp0;
-                aP[4] += gp1 * g.X0; aP[5] += gp1 * g.X1; aP[6] += gp1 * g.X2; aP[7] += gp1;
-                aP[8] += gp2 * g.X0; aP[9] += gp2 * g.X1; aP[10] += gp2 * g.X2; aP[11] += gp2;
-                const float gX0 = Pf[0] * gp0 + Pf[4] * gp1 + Pf[8] * gp2;
-                const float gX1 = Pf[1] * gp0 + Pf[5] * gp1 + Pf[9] * gp2;
-                const float gX2 = Pf[2] * gp0 + Pf[6] * gp1 + Pf[10] * gp2;
-                const float gD = gX0 * g.r0 + gX1 * g.r1 + gX2 * g.r2;
-                gd[i] += -p.range * g.D * g.D * gD;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (act[u]) {
+                    const int i = i0 + u;
+                    const Geo& g = geo[i];
+                    float gix = 0.f, giy = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        // ATen grid_sampler_2d_backward with the out-of-range taps skipped (weight-0 taps)
+                        const float v00 = v[u][ch][0], v01 = bt[u].vx ? v[u][ch][1] : 0.f;
+                        const float v10 = bt[u].vy ? v[u][ch][2] : 0.f;
+                        const float v11 = (bt[u].vx && bt[u].vy) ? v[u][ch][3] : 0.f;
+                        const float dix = -v00 * bt[u].ey + v01 * bt[u].ey - v10 * bt[u].ay + v11 * bt[u].ay;
+                        const float diy = -v00 * bt[u].ex - v01 * bt[u].ax + v10 * bt[u].ex + v11 * bt[u].ax;
+                        gix += G[ch][i] * dix;
+                        giy += G[ch][i] * diy;
+                    }
+                    const float gu = gix * pr[u].mx, gv = giy * pr[u].my;
+                    const float rz = __frcp_rn(pr[u].z);
+                    const float gp0 = gu * rz, gp1 = gv * rz, gp2 = -(gu * pr[u].u + gv * pr[u].v) * rz;
+                    aP[0] += gp0 * g.X0; aP[1] += gp0 * g.X1; aP[2] += gp0 * g.X2; aP[3] += gp0;
+                    aP[4] += gp1 * g.X0; aP[5] += gp1 * g.X1; aP[6] += gp1 * g.X2; aP[7] += gp1;
+                    aP[8] += gp2 * g.X0; aP[9] += gp2 * g.X1; aP[10] += gp2 * g.X2; aP[11] += gp2;
+                    const float gX0 = Pf[0] * gp0 + Pf[4] * gp1 + Pf[8] * gp2;
+                    const float gX1 = Pf[1] * gp0 + Pf[5] * gp1 + Pf[9] * gp2;
+                    const float gX2 = Pf[2] * gp0 + Pf[6] * gp1 + Pf[10] * gp2;
+                    const float gD = gX0 * g.r0 + gX1 * g.r1 + gX2 * g.r2;
+                    gd[i] += -p.range * g.D * g.D * gD;
+                }
             }
         }
 #pragma unroll
@@ -560,7 +637,9 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
     for (int e = tid; e < kTH * ni; e += kNT) {
         const int y = e / ni, ii = e - y * ni, gi = ilo + ii;
         float acc = 0.f;
-        for (int x = 0; x < kTW; ++x) {
+        const int fac = p.fac[s];
+        const int xlo = max(0, (gi - 1) * fac + fac / 2 - 1 - tx0), xhi = min(kTW - 1, (gi + 1) * fac + fac / 2 - tx0);
+        for (int x = xlo; x <= xhi; ++x) {
             const float gval = s_g[y * kTW + x];
             if (s_tx0[x] == gi) acc += (1.f - s_tlx[x]) * gval;
             if (s_tx1[x] == gi) acc += s_tlx[x] * gval;
@@ -572,7 +651,9 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
     for (int e = tid; e < nj * ni; e += kNT) {
         const int jj = e / ni, ii = e - jj * ni, gj = jlo + jj;
         float acc = 0.f;
-        for (int y = 0; y < kTH; ++y) {
+        const int fac = p.fac[s];
+        const int ylo = max(0, (gj - 1) * fac + fac / 2 - 1 - ty0), yhi = min(kTH - 1, (gj + 1) * fac + fac / 2 - ty0);
+        for (int y = ylo; y <= yhi; ++y) {
             const float tv = s_t[y * TP + ii];
             if (s_ty0[y] == gj) acc += (1.f - s_tly[y]) * tv;
             if (s_ty1[y] == gj) acc += s_tly[y] * tv;
