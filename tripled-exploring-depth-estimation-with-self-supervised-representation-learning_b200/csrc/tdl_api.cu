@@ -1,6 +1,7 @@
 // extern "C" entry points of libtdl.so (see include/tdl.h): argument validation,
 // workspace carving and kernel sequencing.  No torch types, no allocation, no host sync.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -82,6 +83,7 @@ int check_photo(const tdl_photo_args* a, bool bwd, PhotoDev* d) {
     for (int s = 0; s < a->nscales; ++s) d->J[s] = reinterpret_cast<float*>(ws + L.j_off[s]);
     d->argmin = reinterpret_cast<unsigned char*>(ws + L.argmin_off);
     d->automask = a->automask != 0;
+    d->use_tma = getenv("TDL_NO_TMA") == nullptr;
     d->align_corners = a->align_corners != 0;
     d->min_disp = (float)(1.0 / a->max_depth);
     d->range = (float)(1.0 / a->min_depth - 1.0 / a->max_depth);

@@ -18,6 +18,7 @@ struct PhotoDev {
     int dh[TDL_MAX_SCALES], dw[TDL_MAX_SCALES], fac[TDL_MAX_SCALES];
     float sy[TDL_MAX_SCALES], sx[TDL_MAX_SCALES];     // dh/H, dw/W (F.interpolate scale)
     int automask, align_corners;
+    int use_tma;                 // stage image tiles with TMA box copies when the tensors allow it
     float min_disp, range;
     uint64_t seed;
     const float* target;

@@ -20,6 +20,7 @@
 // mono/model/mono_fm/layers.py:57-107 (see include/tdl.h).
 #include "tdl_common.cuh"
 #include "tdl_internal.h"
+#include "tdl_tma.cuh"
 
 namespace tdl {
 
@@ -316,15 +317,22 @@ __global__ void __launch_bounds__(kNT, 2) photo_fwd_kernel(const PhotoDev p) {
 
 // ------------------------------------------------------------------------------------------------
 // Backward.
-template <int S>
-__global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
-    constexpr int QW = kTW + 4, QH = kTH + 4, QPLANE = QW * QH;       // halo 2
+// Backward tile: halo 2 in y, and in x a left margin of 4 so that the TMA box starts on a 16-byte boundary
+// (the innermost box coordinate must keep 16-byte alignment -- tx0 - 2 raised "illegal instruction" on B200).
+constexpr int kQX0 = 4, kQY0 = 2;                                     // tile origin inside the staged box
+constexpr int kQW = kTW + 8, kQH = kTH + 4, kQPLANE = kQW * kQH;
+constexpr int kQGROUP = (3 * kQPLANE + 31) / 32 * 32;                // 3 planes, 128-byte multiple (TMA destination)
+
+template <int S, bool kTMA>
+__global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, const __grid_constant__ PhotoMaps maps) {
+    constexpr int QW = kQW, QH = kQH, QPLANE = kQPLANE, QGROUP = kQGROUP;
     constexpr int PW = kTW + 2, PH = kTH + 2;                           // window centres: halo 1
-    extern __shared__ float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* s_tgt = smem;                         // [3][QPLANE]
-    float* s_wrp = s_tgt + 3 * QPLANE;           // [S][3][QPLANE]
-    float* s_coef = s_wrp + S * 3 * QPLANE;      // [3 ch][3 coef][QPLANE]
+    float* s_wrp = s_tgt + QGROUP;               // [S] groups of [3][QPLANE]
+    float* s_coef = s_wrp + S * QGROUP;          // [3 ch][3 coef][QPLANE]
     unsigned char* s_mask = reinterpret_cast<unsigned char*>(s_coef + 9 * QPLANE);   // [QPLANE]
+    __shared__ uint64_t s_bar;
     __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
     __shared__ float s_dP[TDL_MAX_SRC * 12];
     __shared__ int s_cnt[TDL_MAX_SRC];
@@ -349,7 +357,15 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
     const float* s_iK = s_cam + TDL_MAX_SRC * 12;
     if (tid < kTW) up_index(tx0 + tid, p.sx[s], w, s_tx0[tid], s_tx1[tid], s_tlx[tid]);
     if (tid >= 32 && tid < 32 + kTH) up_index(ty0 + tid - 32, p.sy[s], h, s_ty0[tid - 32], s_ty1[tid - 32], s_tly[tid - 32]);
+    if (kTMA && tid == 0) mbar_init(&s_bar, 1);
     __syncthreads();
+    if (kTMA && tid == 0) {
+        // one elected thread stages the target and the S warped tiles (halo 2) with 3-D TMA box copies
+        mbar_arrive_expect_tx(&s_bar, (uint32_t)((1 + S) * 3 * QPLANE * sizeof(float)));
+        tma_load_3d(s_tgt, &maps.tgt, &s_bar, tx0 - kQX0, ty0 - kQY0, b * 3);
+#pragma unroll
+        for (int f = 0; f < S; ++f) tma_load_3d(s_wrp + f * QGROUP, &maps.img[s * S + f], &s_bar, tx0 - kQX0, ty0 - kQY0, b * 3);
+    }
 
     const DepthParams dp{p.min_disp, p.range};
     const float* db = p.disp[s] + (size_t)b * h * w;
@@ -363,14 +379,41 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
         const float* tb = p.target + (size_t)b * 3 * HW;
         const bool have_warped = p.warped[s][0] != nullptr;
         constexpr int NIT = (QPLANE + kNT - 1) / kNT;
-        if (have_warped) {
+        if (kTMA) {
+            for (int i = tid; i < QPLANE; i += kNT) {
+                const int r = i / QW, c = i - r * QW;
+                const int ry = ty0 - 2 + r, rx = tx0 - kQX0 + c;
+                const bool inside = ry >= 0 && ry < H && rx >= 0 && rx < W;
+                s_mask[i] = inside ? am[(size_t)ry * W + rx] : (unsigned char)255;
+            }
+            mbar_wait(&s_bar, 0);
+            // nn.ReflectionPad2d(1): the zero-filled cells one pixel outside the image take their mirror value
+            const bool bl = tx0 == 0, br = tx0 + kTW >= W, bt_ = ty0 == 0, bb = ty0 + kTH >= H;
+            if (bl || br) {
+                for (int e = tid; e < (1 + S) * 3 * QH; e += kNT) {
+                    const int g = e / (3 * QH), rem = e - g * 3 * QH, ch = rem / QH, r = rem - ch * QH;
+                    float* row = smem + g * QGROUP + ch * QPLANE + r * QW;
+                    if (bl) row[kQX0 - 1] = row[kQX0 + 1];
+                    if (br) row[W - tx0 + kQX0] = row[W - tx0 + kQX0 - 2];
+                }
+            }
+            if (bt_ || bb) {
+                __syncthreads();
+                for (int e = tid; e < (1 + S) * 3 * QW; e += kNT) {
+                    const int g = e / (3 * QW), rem = e - g * 3 * QW, ch = rem / QW, c = rem - ch * QW;
+                    float* col = smem + g * QGROUP + ch * QPLANE + c;
+                    if (bt_) col[1 * QW] = col[3 * QW];
+                    if (bb) col[(H - ty0 + 2) * QW] = col[(H - ty0) * QW];
+                }
+            }
+        } else if (have_warped) {
             float tv[NIT][3], wv[NIT][S][3];
             unsigned char mv[NIT];
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int i = min(tid + it * kNT, QPLANE - 1);
                 const int r = i / QW, c = i - r * QW;
-                const int ry = ty0 - 2 + r, rx = tx0 - 2 + c;
+                const int ry = ty0 - 2 + r, rx = tx0 - kQX0 + c;
                 const bool inside = ry >= 0 && ry < H && rx >= 0 && rx < W;
                 const size_t o = (size_t)reflect1(ry, H) * W + reflect1(rx, W);
                 mv[it] = inside ? am[o] : (unsigned char)255;
@@ -393,13 +436,13 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
 #pragma unroll
                     for (int f = 0; f < S; ++f)
 #pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) s_wrp[(f * 3 + ch) * QPLANE + i] = wv[it][f][ch];
+                        for (int ch = 0; ch < 3; ++ch) s_wrp[f * QGROUP + ch * QPLANE + i] = wv[it][f][ch];
                 }
             }
         } else {
             for (int i = tid; i < QPLANE; i += kNT) {
                 const int r = i / QW, c = i - r * QW;
-                const int ry = ty0 - 2 + r, rx = tx0 - 2 + c;
+                const int ry = ty0 - 2 + r, rx = tx0 - kQX0 + c;
                 const bool inside = ry >= 0 && ry < H && rx >= 0 && rx < W;
                 const int py = reflect1(ry, H), px = reflect1(rx, W);
                 const size_t o = (size_t)py * W + px;
@@ -415,7 +458,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
                     const float* sb = p.src[f] + (size_t)b * 3 * HW;
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch)
-                        s_wrp[(f * 3 + ch) * QPLANE + i] = bilin_sample(sb + ch * HW, W, bt);
+                        s_wrp[f * QGROUP + ch * QPLANE + i] = bilin_sample(sb + ch * HW, W, bt);
                 }
             }
         }
@@ -444,7 +487,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
         //      heavy statistics run with full warps and an even share per thread; the others just store zeros.
         for (int i = tid; i < PH * PW; i += kNT) {
             const int r = i / PW, c = i - r * PW;
-            const int q = (r + 1) * QW + (c + 1);
+            const int q = (r + 1) * QW + c + kQX0 - 1;
             if (s_mask[q] == chan) {
                 s_list[atomicAdd(&s_cnt[f], 1)] = (unsigned short)q;
             } else {
@@ -460,7 +503,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
             for (int ch = 0; ch < 3; ++ch) {
                 float cA = 0.f, cB = 0.f, cC = 0.f;
                 {
-                    const float* xs = s_wrp + (f * 3 + ch) * QPLANE + q;
+                    const float* xs = s_wrp + f * QGROUP + ch * QPLANE + q;
                     const float* ys = s_tgt + ch * QPLANE + q;
                     float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
 #pragma unroll
@@ -509,7 +552,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
         //      actually receive gradient from this source frame.
         float G[3][kR];
         {
-            const int qc = lane + 2;                                  // Q column of this thread's pixels
+            const int qc = lane + kQX0;                               // Q column of this thread's pixels
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 float box[3][kR];
@@ -545,7 +588,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p) {
                             box[k][i] += e;
                         }
                     }
-                    const float xv = s_wrp[(f * 3 + ch) * QPLANE + q], yv = s_tgt[ch * QPLANE + q];
+                    const float xv = s_wrp[f * QGROUP + ch * QPLANE + q], yv = s_tgt[ch * QPLANE + q];
                     float g = box[0][i] + 2.f * xv * box[1][i] + yv * box[2][i];
                     if (s_mask[q] == chan) {
                         const float df = xv - yv;
@@ -678,19 +721,29 @@ static cudaError_t launch_fwd_t(const PhotoDev& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-template <int S>
-static cudaError_t launch_bwd_t(const PhotoDev& p, cudaStream_t st) {
-    constexpr int QPLANE = (kTW + 4) * (kTH + 4);
-    const size_t smem = (size_t)(3 + 3 * S + 9) * QPLANE * sizeof(float) + QPLANE;
+template <int S, bool kTMA>
+static cudaError_t launch_bwd_k(const PhotoDev& p, const PhotoMaps& maps, cudaStream_t st) {
+    const size_t smem = (size_t)((1 + S) * kQGROUP + 9 * kQPLANE) * sizeof(float) + kQPLANE;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(photo_bwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(photo_bwd_kernel<S, kTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     dim3 grid((p.W + kTW - 1) / kTW, (p.H + kTH - 1) / kTH, p.B * p.nscales);
-    photo_bwd_kernel<S><<<grid, kNT, smem, st>>>(p);
+    photo_bwd_kernel<S, kTMA><<<grid, kNT, smem, st>>>(p, maps);
     return cudaGetLastError();
+}
+
+template <int S>
+static cudaError_t launch_bwd_t(const PhotoDev& p, cudaStream_t st) {
+    // TMA path: the forward materialised the warps, every tensor is 16-byte aligned and W % 4 == 0
+    PhotoMaps maps;
+    bool tma = p.use_tma && encode_image_map(&maps.tgt, p.target, p.B * 3, p.H, p.W, kQW, kQH, 3);
+    for (int s = 0; tma && s < p.nscales; ++s)
+        for (int f = 0; tma && f < S; ++f)
+            tma = p.warped[s][f] && encode_image_map(&maps.img[s * S + f], p.warped[s][f], p.B * 3, p.H, p.W, kQW, kQH, 3);
+    return tma ? launch_bwd_k<S, true>(p, maps, st) : launch_bwd_k<S, false>(p, maps, st);
 }
 
 cudaError_t launch_photo_fwd(const PhotoDev& p, cudaStream_t st) {
