@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--frozen-extractor", action="store_true",
                     help="features do not require grad (pretrained, frozen extractor: mono_fm/net.py:24-25)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the full train-step measurement")
+    ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--no-syncbn", action="store_true", help="cfg_kitti_fm sets syncbn = True")
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample")
     return ap.parse_args()
 
@@ -276,6 +279,55 @@ def time_cpu_port(B, H, W, steps, warmup):
     return B * steps / dt, dt / steps
 
 
+# ------------------------------------------------------------------------------------------------ train step
+def train_step_bench(args, device, rank, world, dist_on):
+    """Full cfg_kitti_fm training step (config/cfg_kitti_fm.py: ResNet-50 depth net, ResNet-18 pose net, ResNet-50
+    extractor, Adam 1e-4, grad-clip 35, syncbn) with the fused loss, batch-sharded DDP over NCCL when world > 1.
+    The networks are plain PyTorch (out of the hot path's scope); reported next to the loss-only figure."""
+    tdl = importlib.import_module(PKG)
+    importlib.import_module(PKG + ".nets")
+    B, H, W = args.batch, args.height, args.width
+    opt = opt_dict(B, H, W)
+    opt.update(name="mono_fm", depth_num_layers=50, pose_num_layers=18, extractor_num_layers=50,
+               extractor_pretrained_path=None)
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True
+    model = tdl.MONO.module_dict["mono_fm"](tdl.config.ConfigDict(opt)).to(device).train()
+    n_params = sum(q.numel() for q in model.parameters() if q.requires_grad)
+    syncbn = dist_on and not args.no_syncbn
+    if dist_on:
+        if syncbn:
+            model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index], gradient_as_bucket_view=True)
+    optim = torch.optim.Adam([q for q in model.parameters() if q.requires_grad], lr=1e-4, weight_decay=0)
+    host = make_host_workload(B, H, W, rank_seed(rank))
+    inputs = {}
+    for k, v in host.items():
+        if k[0] == "in":
+            inputs[k[1]] = v.to(device)
+    for f in FRAME_IDS:
+        inputs[("color_aug", f, 0)] = inputs[("color", f, 0)]
+
+    def step():
+        optim.zero_grad(set_to_none=True)
+        _, loss_dict = model(inputs)
+        loss = loss_dict.total()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 35.0)
+        optim.step()
+        return loss
+
+    for _ in range(3):
+        loss = step()
+    ms = timed_region(step, args.train_steps, device, dist_on)
+    return {"images_per_s": round(whole_job_images_per_s(world, B, args.train_steps, ms), 1),
+            "ms_per_step": round(ms / args.train_steps, 3), "steps": args.train_steps,
+            "model": "mono_fm (cfg_kitti_fm): ResNet-50 depth + ResNet-18 pose + ResNet-50 extractor (level 0), "
+                     f"{n_params / 1e6:.1f} M trainable params, eager PyTorch fp32 networks + fused loss, Adam",
+            "parallelism": f"DDP x{world} (NCCL all-reduce of gradients" + (", SyncBatchNorm)" if syncbn else ")"),
+            "final_loss": float(loss)}
+
+
 def config_dict(args, trainable):
     return {"workload": f"mono_fm loss fwd+bwd (cfg_kitti_fm): {args.height}x{args.width}, batch {args.batch}/GPU, "
                         f"frames [0,-1,1], 4 scales, {FEAT_C}-ch features at H/2xW/2, "
@@ -390,6 +442,12 @@ def main():
     ms_e2e = timed_region(lambda: e2e_loop(e2e_steps), 1, device, dist_on)
     e2e_value = whole_job_images_per_s(world, B, e2e_steps, ms_e2e)
 
+    train = None
+    if not args.no_train:
+        del step2, sets
+        torch.cuda.empty_cache()
+        train = train_step_bench(args, device, rank, world, dist_on)
+
     if rank != 0:
         if dist_on:
             torch.distributed.destroy_process_group()
@@ -446,7 +504,7 @@ def main():
                     "d2h_bytes_per_step": step.losses_host.numel() * 4, "ms_per_step": round(ms_e2e / e2e_steps, 4),
                     "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu}
+            "roofline": roofline, "cpu_baseline": cpu, "train_step": train}
     print(json.dumps(line))
     if dist_on:
         torch.distributed.destroy_process_group()

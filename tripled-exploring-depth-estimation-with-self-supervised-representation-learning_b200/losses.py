@@ -150,8 +150,10 @@ class ViewSynthesisLossMixin:
         return res[0][0], (res[1 + len(frames)] if cfg.materialize else None)
 
     def _extract(self, img):
+        """``extractor(img)[0]`` (mono/model/mono_fm/net.py:113,197).  Encoders that can stop after their first
+        level (``first``) are not run through the four residual stages whose outputs the loss never reads."""
         ext = getattr(self, "extractor", None) or getattr(self, "Encoder")
-        return ext(img)[0]
+        return ext.first(img) if hasattr(ext, "first") else ext(img)[0]
 
     def generate_features_pred(self, inputs, outputs):
         """mono/model/mono_fm/net.py:172-199 (stand-alone: warped features, no autograd history)."""
