@@ -26,7 +26,7 @@ inline bool pow2_factor(int big, int small, int* fac) {
 }
 
 struct PhotoWsLayout {
-    uint64_t acc_off, j_off[TDL_MAX_SCALES], argmin_off, total;
+    uint64_t acc_off, j_off[TDL_MAX_SCALES], w_off[TDL_MAX_SCALES], argmin_off, total;
 };
 
 PhotoWsLayout photo_layout(int B, int H, int W, int nscales, const int32_t* dh, const int32_t* dw) {
@@ -37,6 +37,8 @@ PhotoWsLayout photo_layout(int B, int H, int W, int nscales, const int32_t* dh, 
     for (int s = 0; s < TDL_MAX_SCALES; ++s) {
         L.j_off[s] = off;
         if (s < nscales) off = align_up(off + (uint64_t)B * 3 * dh[s] * dw[s] * sizeof(float), 256);
+        L.w_off[s] = off;
+        if (s < nscales) off = align_up(off + (uint64_t)B * 6 * dh[s] * dw[s] * sizeof(float), 256);
     }
     L.argmin_off = off;
     off = align_up(off + (uint64_t)nscales * B * H * W, 256);
@@ -80,7 +82,10 @@ int check_photo(const tdl_photo_args* a, bool bwd, PhotoDev* d) {
     if (a->workspace_bytes < L.total) return TDL_ERR_WORKSPACE;
     char* ws = static_cast<char*>(a->workspace);
     d->acc = reinterpret_cast<double*>(ws + L.acc_off);
-    for (int s = 0; s < a->nscales; ++s) d->J[s] = reinterpret_cast<float*>(ws + L.j_off[s]);
+    for (int s = 0; s < a->nscales; ++s) {
+        d->J[s] = reinterpret_cast<float*>(ws + L.j_off[s]);
+        d->Wt[s] = reinterpret_cast<float*>(ws + L.w_off[s]);
+    }
     d->argmin = reinterpret_cast<unsigned char*>(ws + L.argmin_off);
     d->automask = a->automask != 0;
     d->use_tma = getenv("TDL_NO_TMA") == nullptr;
@@ -100,7 +105,7 @@ void photo_smooth_levels(const tdl_photo_args* a, const PhotoDev& d, bool bwd, S
     for (int s = 0; s < a->nscales; ++s) {
         SmoothLevel& L = sm->lv[s];
         L.C = 1; L.h = d.dh[s]; L.w = d.dw[s];
-        L.x = d.disp[s]; L.J = d.J[s];
+        L.x = d.disp[s]; L.J = d.J[s]; L.Wt = d.Wt[s];
         L.acc = d.acc + (size_t)s * a->B * 4; L.acc_stride = 4;
         L.norm = a->disp_norm != 0;
         L.alpha = a->smooth_alpha;
@@ -334,7 +339,8 @@ int tdl_feat_bwd(const tdl_feat_args* a, tdl_stream_t stream) {
 uint64_t tdl_edge_ws_bytes(int32_t B, int32_t C, int32_t h, int32_t w) {
     (void)C;
     if (B < 1 || h < 1 || w < 1) return 0;
-    return align_up((uint64_t)B * 4 * sizeof(double), 256) + align_up((uint64_t)B * 3 * h * w * sizeof(float), 256);
+    return align_up((uint64_t)B * 4 * sizeof(double), 256) + align_up((uint64_t)B * 3 * h * w * sizeof(float), 256) +
+           align_up((uint64_t)B * 6 * h * w * sizeof(float), 256);
 }
 
 static int check_edge(const tdl_edge_args* a, bool bwd, SmoothDev* sm, float** J) {
@@ -353,6 +359,7 @@ static int check_edge(const tdl_edge_args* a, bool bwd, SmoothDev* sm, float** J
     SmoothLevel& L = sm->lv[0];
     L.C = a->C; L.h = a->h; L.w = a->w;
     L.x = a->feature; L.J = *J;
+    L.Wt = *J + align_up((uint64_t)a->B * 3 * a->h * a->w * sizeof(float), 256) / sizeof(float);
     L.acc = reinterpret_cast<double*>(ws); L.acc_stride = 4;
     L.norm = 0; L.alpha = a->alpha;
     L.first_coef = a->first_coef; L.second_coef = a->second_coef;

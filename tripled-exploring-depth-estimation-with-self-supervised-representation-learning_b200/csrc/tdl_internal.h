@@ -33,6 +33,7 @@ struct PhotoDev {
     double* acc;                 // [nscales][B][4]: photo sum, disp sum, smooth first, smooth second
     unsigned char* argmin;       // [nscales][B][H][W]
     float* J[TDL_MAX_SCALES];    // area-downsampled target (B,3,dh,dw)
+    float* Wt[TDL_MAX_SCALES];   // smoothness edge weights (B,6,dh,dw)
     // backward
     const float* dlosses;
     float photo_coef[TDL_MAX_SCALES];
@@ -45,6 +46,7 @@ struct SmoothLevel {
     int C, h, w;
     const float* x;        // (B,C,h,w)
     const float* J;        // (B,3,h,w) area-downsampled image
+    float* Wt;             // (B,6,h,w) edge weights exp(-alpha*mean_c|stencil(J)|): written by the forward, re-read by the backward
     double* acc;           // per image b: acc[b*stride + 2] += first, acc[b*stride + 3] += second;
                            //              acc[b*stride + 1] holds sum(x) when norm
     int acc_stride;

@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(kSmoothNT) smooth_fwd_kernel(const SmoothDev p
     if (pix < h * w) {
         const int j = pix / w, i = pix - j * w;
         const Stencil6 wt = edge_weights(L.J + (size_t)b * 3 * h * w, j, i, h, w, L.alpha);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) L.Wt[((size_t)b * 6 + k) * h * w + pix] = wt.v[k];       // for the backward
         const Counts cn = inv_counts(p.B, C, h, w);
         const float den = L.norm ? norm_denominator(L, b) : 1.f;
         for (int c = 0; c < C; ++c) {
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(kSmoothNT) smooth_fwd_kernel(const SmoothDev p
             const Stencil6 s = stencils(
                 [&](int jj, int ii) {
                     const float v = __ldg(pl + (size_t)jj * w + ii);
-                    return L.norm ? __fdiv_rn(v, den) : v;
+                    return L.norm ? div_rn(v, den) : v;
                 },
                 j, i, h, w);
             first += fabsf(s.v[0]) * wt.v[0] * cn.inv[0] + fabsf(s.v[1]) * wt.v[1] * cn.inv[1];
@@ -138,7 +140,6 @@ __global__ void __launch_bounds__(kSmoothNT) smooth_bwd_kernel(const SmoothDev p
     const int pix = blockIdx.x * kSmoothNT + threadIdx.x;
     if (pix >= h * w) return;
     const int j = pix / w, i = pix - j * w;
-    const float* Jb = L.J + (size_t)b * 3 * h * w;
     const Counts cn = inv_counts(p.B, C, h, w);
     const float up = __ldg(L.dloss);
     const float c1 = up * L.first_coef, c2 = up * L.second_coef;
@@ -161,7 +162,9 @@ __global__ void __launch_bounds__(kSmoothNT) smooth_bwd_kernel(const SmoothDev p
     for (int a = 0; a < 6; ++a) {
         const int jj = j + aj[a], ii = i + ai[a];
         if (jj >= 0 && ii >= 0) {
-            wt[a] = edge_weights(Jb, jj, ii, h, w, L.alpha);
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                wt[a].v[k] = (cf[a][k] != 0.f) ? __ldg(L.Wt + ((size_t)b * 6 + k) * h * w + (size_t)jj * w + ii) : 0.f;
         } else {
 #pragma unroll
             for (int k = 0; k < 6; ++k) wt[a].v[k] = 0.f;
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(kSmoothNT) smooth_bwd_kernel(const SmoothDev p
         const float* pl = L.x + ((size_t)b * C + c) * h * w;
         auto ld = [&](int jj, int ii) {
             const float v = __ldg(pl + (size_t)jj * w + ii);
-            return L.norm ? __fdiv_rn(v, den) : v;
+            return L.norm ? div_rn(v, den) : v;
         };
         float g = 0.f;
 #pragma unroll
