@@ -34,10 +34,22 @@ TDL_DEV float div9(float s) {
 // instructions): q0 = n * rcp(d) refined by one Newton step on the residual.  For the operand ranges of
 // this path (|d| in [1e-7, 1e4], no denormals, no overflow) the result equals the IEEE quotient; ncu (round 1)
 // attributed 22 % of the forward's instructions to the 140 divisions per pixel.
+TDL_DEV float rcp_approx(float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));      // MUFU.RCP, 1 ulp
+    return r;
+}
 TDL_DEV float div_rn(float n, float d) {
-    const float r = __frcp_rn(d);
+    const float r = rcp_approx(d);
     const float q = n * r;
     return fmaf(fmaf(-d, q, n), r, q);
+}
+// sqrt(x) for x in [1e-7, 1e2]: rsqrt seed + one Newton step on the residual (correctly rounded except for
+// rare last-bit ties); __fsqrt_rn's IEEE sequence was 5 % of the forward's instructions (line profile, r1)
+TDL_DEV float sqrt_fast(float x) {
+    const float r = rsqrtf(x);
+    const float s = x * r;
+    return fmaf(fmaf(-s, s, x), 0.5f * r, s);
 }
 // division by a constant whose reciprocal rc = fl(1/c) is known
 TDL_DEV float div_const(float n, float c, float rc) {
@@ -129,7 +141,7 @@ TDL_DEV Proj project(const Geo& g, const float* P, int H, int W, int align_corne
     const float p2 = P[8] * g.X0 + P[9] * g.X1 + P[10] * g.X2 + P[11];
     o.z = __fadd_rn(p2, kProjEps);                                            // layers.py:76
     {
-        const float rz = __frcp_rn(o.z);                                      // both quotients share rcp(z)
+        const float rz = rcp_approx(o.z);                                     // both quotients share rcp(z)
         const float qu = p0 * rz, qv = p1 * rz;
         o.u = fmaf(fmaf(-o.z, qu, p0), rz, qu);
         o.v = fmaf(fmaf(-o.z, qv, p1), rz, qv);
@@ -221,6 +233,44 @@ TDL_DEV float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Sums 12 per-lane values over the warp with 16 shuffles instead of 60: at every butterfly step a lane keeps one half of
+// the (remaining) values and hands the other half to its partner.  On return lane l (l < 12 after the value-splitting
+// steps, see below) holds the total of value `slot`; returns that slot index, or -1 when the lane holds nothing.
+TDL_DEV int warp_sum12(const float in[12], float& total) {
+    const int lane = threadIdx.x & 31;
+    float a[8];
+    // step 1 (xor 16): 12 -> 6 values (+2 zero pads -> 8 slots of which 6 used)
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const float keep = hi ? in[6 + k] : in[k], give = hi ? in[k] : in[6 + k];
+            a[k] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+        }
+    }
+    // step 2 (xor 8): 6 -> 3
+    float b3[3];
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float keep = hi ? a[3 + k] : a[k], give = hi ? a[k] : a[3 + k];
+            b3[k] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+        }
+    }
+    // steps 3-5 (xor 4, 2, 1): plain butterfly on the 3 remaining values
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) b3[k] += __shfl_xor_sync(0xffffffffu, b3[k], o);
+    }
+    // lane layout: bit4 selects {0..5 | 6..11}, bit3 selects {first | second} triple; lanes 0, 8, 16, 24 publish
+    const int base = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0);
+    const int sub = lane & 7;                   // lanes sub = 0,1,2 of each octet publish one value each
+    total = sub == 0 ? b3[0] : (sub == 1 ? b3[1] : b3[2]);
+    return sub < 3 ? base + sub : -1;
 }
 
 // Sums `v` over the block; result valid in thread 0.  `scratch` holds >= 32 floats.

@@ -102,7 +102,7 @@ TDL_DEV void strip_ssim_l1(const float* __restrict__ xs, const float* __restrict
         }
         if (j >= 1 && j <= kR) {                                                           // centre pixel of window j-1
             const float df = __fsub_rn(y1, x1);                                            // net.py:57
-            l1_acc[j - 1] += __fsqrt_rn(__fadd_rn(__fmul_rn(df, df), kL1Eps2));
+            l1_acc[j - 1] += sqrt_fast(__fadd_rn(__fmul_rn(df, df), kL1Eps2));
         }
         if (j >= 2) {
             const int i = j - 2;
@@ -131,13 +131,26 @@ TDL_DEV void strip_reprojection(const float* __restrict__ pred3, const float* __
         rho[i] = __fadd_rn(__fmul_rn(0.85f, div3(sa[i])), __fmul_rn(0.15f, div3(la[i])));
 }
 
-TDL_DEV float automask_noise(const PhotoDev& p, int s, int f, int b, size_t pix, size_t HW) {
-    const float* n = p.noise[s][f];
-    if (n) return __ldg(n + (size_t)b * HW + pix);
+// N(0,1) draws for the S identity channels of one pixel at one scale: the caller's tensors when given
+// (reference parity), else ONE Philox4x32-10 call -> two Box-Muller pairs -> up to four normals.
+template <int S>
+TDL_DEV void automask_noise(const PhotoDev& p, int s, int b, size_t pix, size_t HW, float out[S]) {
+    if (p.noise[s][0]) {
+#pragma unroll
+        for (int f = 0; f < S; ++f) out[f] = __ldg(p.noise[s][f] + (size_t)b * HW + pix);
+        return;
+    }
     const unsigned long long idx = (unsigned long long)b * HW + pix;
-    const uint4 r = philox4x32(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)(s * TDL_MAX_SRC + f), 0u),
+    const uint4 r = philox4x32(make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)s, 0u),
                                make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-    return box_muller(r.x, r.y).x;
+    const float2 n01 = box_muller(r.x, r.y);
+    out[0] = n01.x;
+    if (S > 1) out[1] = n01.y;
+    if (S > 2) {
+        const float2 n23 = box_muller(r.z, r.w);
+        out[2] = n23.x;
+        if (S > 3) out[S - 1] = n23.y;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -258,20 +271,22 @@ __global__ void __launch_bounds__(kNT, 2) photo_fwd_kernel(const PhotoDev p) {
         int chan = 0;
         if (p.automask) {
 #pragma unroll
-            for (int f = 0; f < S; ++f) {
+            for (int i = 0; i < kR; ++i) {
+                const int gy = ty0 + r0 + i;
+                float nz[S];
 #pragma unroll
-                for (int i = 0; i < kR; ++i) {
-                    const int gy = ty0 + r0 + i;
-                    float v = rho_id[f][i];
-                    if (gx < W && gy < H)
-                        v = __fadd_rn(v, __fmul_rn(automask_noise(p, s, f, b, (size_t)gy * W + gx, HW), 1e-5f));
-                    if (arg[i] < 0 || v < best[i]) {
+                for (int f = 0; f < S; ++f) nz[f] = 0.f;
+                if (gx < W && gy < H) automask_noise<S>(p, s, b, (size_t)gy * W + gx, HW, nz);
+#pragma unroll
+                for (int f = 0; f < S; ++f) {
+                    const float v = __fadd_rn(rho_id[f][i], __fmul_rn(nz[f], 1e-5f));     // net.py:94
+                    if (f == 0 || v < best[i]) {
                         best[i] = v;
-                        arg[i] = chan;
+                        arg[i] = f;
                     }
                 }
-                ++chan;
             }
+            chan = S;
         }
 #pragma unroll
         for (int f = 0; f < S; ++f) {
@@ -659,10 +674,10 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
                 }
             }
         }
-#pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            const float v = warp_sum(aP[k]);
-            if (lane == 0) atomicAdd(&s_dP[f * 12 + k], v);
+        {
+            float tot;
+            const int slot = warp_sum12(aP, tot);
+            if (slot >= 0) atomicAdd(&s_dP[f * 12 + slot], tot);
         }
         __syncthreads();          // s_coef is rewritten by the next source frame
     }
