@@ -56,34 +56,43 @@ __global__ void __launch_bounds__(kFeatNT) feat_fwd_kernel(const FeatDev p) {
             o11[f] = y1 * w + x1;
         }
         constexpr int CB = (S <= 2) ? 8 : 4;                       // channels per batch
-        const float* tb = p.tgt + (size_t)b * C * hw + pix;
+        // block-uniform 64-bit bases + 32-bit per-thread offsets: one integer add per load / store
+        const unsigned uhw = (unsigned)hw;
+        const float* tbase = p.tgt + (size_t)b * C * hw;
+        const float* sbase[S];
+        float* wbase[S];
+#pragma unroll
+        for (int f = 0; f < S; ++f) {
+            sbase[f] = p.src[f] + (size_t)b * C * hw;
+            wbase[f] = p.warped[f] ? p.warped[f] + (size_t)b * C * hw : nullptr;
+        }
         for (int c0 = 0; c0 < C; c0 += CB) {
             float t[CB], v[S][CB][4];
 #pragma unroll
             for (int j = 0; j < CB; ++j) {
-                const int c = min(c0 + j, C - 1);
-                t[j] = __ldg(tb + (size_t)c * hw);
+                const unsigned co = (unsigned)min(c0 + j, C - 1) * uhw;
+                t[j] = __ldg(tbase + (co + (unsigned)pix));
 #pragma unroll
                 for (int f = 0; f < S; ++f) {
-                    const float* pl = p.src[f] + ((size_t)b * C + c) * hw;
-                    v[f][j][0] = __ldg(pl + o00[f]);
-                    v[f][j][1] = __ldg(pl + o01[f]);
-                    v[f][j][2] = __ldg(pl + o10[f]);
-                    v[f][j][3] = __ldg(pl + o11[f]);
+                    v[f][j][0] = __ldg(sbase[f] + (co + (unsigned)o00[f]));
+                    v[f][j][1] = __ldg(sbase[f] + (co + (unsigned)o01[f]));
+                    v[f][j][2] = __ldg(sbase[f] + (co + (unsigned)o10[f]));
+                    v[f][j][3] = __ldg(sbase[f] + (co + (unsigned)o11[f]));
                 }
             }
 #pragma unroll
             for (int j = 0; j < CB; ++j) {
                 if (c0 + j < C) {
+                    const unsigned co = (unsigned)(c0 + j) * uhw + (unsigned)pix;
 #pragma unroll
                     for (int f = 0; f < S; ++f) {
                         float val = v[f][j][0] * bt[f].nw;
                         val += v[f][j][1] * bt[f].ne;
                         val += v[f][j][2] * bt[f].sw;
                         val += v[f][j][3] * bt[f].se;
-                        if (p.warped[f]) p.warped[f][((size_t)b * C + c0 + j) * hw + pix] = val;
+                        if (wbase[f]) wbase[f][co] = val;
                         const float df = __fsub_rn(val, t[j]);                     // robust_l1(tgt_f, src_f)
-                        acc[f] += __fsqrt_rn(__fadd_rn(__fmul_rn(df, df), kL1Eps2));
+                        acc[f] += sqrt_fast(__fadd_rn(__fmul_rn(df, df), kL1Eps2));
                     }
                 }
             }
@@ -167,24 +176,28 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
     }
 
     constexpr int CB = 8;
-    const float* tb = p.tgt + (size_t)b * C * hw + pix;
+    // block-uniform 64-bit bases + 32-bit per-thread offsets (one integer add per access)
+    const unsigned uhw = (unsigned)hw, upix = (unsigned)min(pix, (int)hw - 1);
+    const float* tbase = p.tgt + (size_t)b * C * hw;
+    const float* sbb = sb + (size_t)b * C * hw;
+    float* dtb = (kGradFeat && p.d_tgt) ? p.d_tgt + (size_t)b * C * hw : nullptr;
+    float* dsbb = (kGradFeat && dsb) ? dsb + (size_t)b * C * hw : nullptr;
     float gix = 0.f, giy = 0.f;
     for (int c0 = 0; c0 < C; c0 += CB) {
         float t[CB], v[CB][4];
 #pragma unroll
         for (int j = 0; j < CB; ++j) {
-            const int c = min(c0 + j, C - 1);
-            const float* pl = sb + ((size_t)b * C + c) * hw;
-            t[j] = active ? __ldg(tb + (size_t)c * hw) : 0.f;
-            v[j][0] = active ? __ldg(pl + o00) : 0.f;
-            v[j][1] = active ? __ldg(pl + o01) : 0.f;
-            v[j][2] = active ? __ldg(pl + o10) : 0.f;
-            v[j][3] = active ? __ldg(pl + o11) : 0.f;
+            const unsigned co = (unsigned)min(c0 + j, C - 1) * uhw;
+            t[j] = active ? __ldg(tbase + (co + upix)) : 0.f;
+            v[j][0] = active ? __ldg(sbb + (co + (unsigned)o00)) : 0.f;
+            v[j][1] = active ? __ldg(sbb + (co + (unsigned)o01)) : 0.f;
+            v[j][2] = active ? __ldg(sbb + (co + (unsigned)o10)) : 0.f;
+            v[j][3] = active ? __ldg(sbb + (co + (unsigned)o11)) : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < CB; ++j) {
             if (c0 + j < C) {                                             // uniform across the warp
-                const size_t plane = ((size_t)b * C + c0 + j) * hw;
+                const unsigned co = (unsigned)(c0 + j) * uhw;
                 // zero weight <=> clamped tap: same arithmetic as bilin_sample_grad with the tap skipped
                 const float v00 = v[j][0], v01 = bt.vx ? v[j][1] : 0.f, v10 = bt.vy ? v[j][2] : 0.f;
                 const float v11 = (bt.vx && bt.vy) ? v[j][3] : 0.f;
@@ -196,8 +209,8 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
                 gix += gvv * dix;
                 giy += gvv * diy;
                 if (kGradFeat) {
-                    if (p.d_tgt && active) p.d_tgt[plane + pix] = -gvv;
-                    if (dsb) {
+                    if (dtb && active) dtb[co + upix] = -gvv;
+                    if (dsbb) {
                         float top = gvv * bt.nw, bot = gvv * bt.sw;
                         const float e_top = gvv * bt.ne, e_bot = gvv * bt.se;
                         const float in_top = __shfl_up_sync(0xffffffffu, e_top, 1);
@@ -207,12 +220,11 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
                             bot += in_bot;
                         }
                         if (active) {
-                            float* q = dsb + plane;
-                            atomicAdd(q + o00, top);
-                            if (bt.vy) atomicAdd(q + o10, bot);
+                            atomicAdd(dsbb + (co + (unsigned)o00), top);
+                            if (bt.vy) atomicAdd(dsbb + (co + (unsigned)o10), bot);
                             if (!absorbed && bt.vx) {
-                                atomicAdd(q + o01, e_top);
-                                if (bt.vy) atomicAdd(q + o11, e_bot);
+                                atomicAdd(dsbb + (co + (unsigned)o01), e_top);
+                                if (bt.vy) atomicAdd(dsbb + (co + (unsigned)o11), e_bot);
                             }
                         }
                     }
