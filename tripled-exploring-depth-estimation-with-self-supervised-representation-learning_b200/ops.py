@@ -118,6 +118,7 @@ class PhotometricSmoothLoss(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(L.tdl_photo_fwd(C.byref(a), _stream()), "tdl_photo_fwd")
         ctx.cfg = cfg
+        ctx.set_materialize_grads(False)      # no zero-filled "gradients" for the warped images / index maps
         ctx.n_warped = len(warped)
         # the backward re-reads the materialised warps instead of re-projecting the tile halo
         ctx.save_for_backward(target, P, invK, ws, *srcs, *disps, *warped)
@@ -130,6 +131,8 @@ class PhotometricSmoothLoss(torch.autograd.Function):
         cfg = ctx.cfg
         S, n = cfg.n_src, cfg.n_scales
         target, P, invK, ws = ctx.saved_tensors[:4]
+        if g_losses is None:
+            g_losses = torch.zeros(2 * n, dtype=torch.float32, device=target.device)
         srcs = ctx.saved_tensors[4:4 + S]
         disps = ctx.saved_tensors[4 + S:4 + S + n]
         warped = ctx.saved_tensors[4 + S + n:4 + S + n + ctx.n_warped]
@@ -220,6 +223,7 @@ class FeatureMetricLoss(torch.autograd.Function):
         with torch.cuda.device(tgt.device):
             _lib.check(L.tdl_feat_fwd(C.byref(a), _stream()), "tdl_feat_fwd")
         ctx.cfg = cfg
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(tgt, disp, P, invK, ws, *srcs)
         ctx.mark_non_differentiable(*warped, *extra)
         return (loss, *warped, *extra)
@@ -231,6 +235,8 @@ class FeatureMetricLoss(torch.autograd.Function):
         S = cfg.n_src
         tgt, disp, P, invK, ws = ctx.saved_tensors[:5]
         srcs = ctx.saved_tensors[5:5 + S]
+        if g_loss is None:
+            g_loss = torch.zeros(1, dtype=torch.float32, device=tgt.device)
         B, Cc, h, w = tgt.shape
         need = ctx.needs_input_grad            # (cfg, tgt, disp, P, invK, *srcs)
         a = FeatArgs()
