@@ -82,8 +82,12 @@ def algorithmic_bytes(B, H, W, S, C, n_scales, trainable_feat, materialize=True,
     else:
         feat_bwd = C * N * (1 + S)
         memset_dsrc = 0
-    per_image = dict(photo_fwd=photo_fwd, photo_bwd=photo_bwd, feat_fwd=feat_fwd, feat_bwd=feat_bwd,
-                     memset_dsrc=memset_dsrc)
+    # split forward: the warp kernel reads disp + sources and writes the warps; the scoring kernel reads target,
+    # sources (identity terms) and the warps back, and writes min_index
+    photo_warp = sum(12 * S * N + 12 * S * N + 4 * n for n in ns)
+    photo_score = sum(12 * N + 12 * S * N + 12 * S * N + 8 * N for _ in ns)
+    per_image = dict(photo_fwd=photo_fwd, photo_warp=photo_warp, photo_score=photo_score, photo_bwd=photo_bwd,
+                     feat_fwd=feat_fwd, feat_bwd=feat_bwd, memset_dsrc=memset_dsrc)
     return {k: v * B for k, v in per_image.items()}
 
 
@@ -415,7 +419,7 @@ def run():
     for _ in range(prof_steps):
         step.run_eager()
     kern = tdl._lib.profile_end()
-    launches_per_step = sum(tdl._lib.launch_count(e) for e in ("tdl_photo_fwd", "tdl_photo_bwd", "tdl_feat_fwd", "tdl_feat_bwd"))
+    launches_per_step = sum(n for k, (n, _) in kern.items() if not k.startswith("memset")) // prof_steps
 
     # ---- value: device-resident inputs, CUDA-graph replay
     step.capture()
@@ -499,7 +503,7 @@ def run():
         r["share"] = round(r["us_per_step"] / tot_us, 3)
     dom = max((k for k in kernels if "alg_bytes" in kernels[k]), key=lambda k: kernels[k]["us_per_step"])
     achieved = kernels[dom]["gbs"]
-    total_alg = sum(alg.values())
+    total_alg = sum(alg[k] for k in ("photo_fwd", "photo_bwd", "feat_fwd", "feat_bwd", "memset_dsrc"))
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed

@@ -89,7 +89,7 @@ def test_argument_errors_without_a_gpu(lib, tdl):
     assert need >= 4 * 64 * 96 + 4 * 4 * 8                           # argmin masks + accumulators at least
     assert lib.tdl_feat_fwd(None, None) == -1
     assert lib.tdl_edge_smooth_fwd(None, None) == -1
-    assert lib.tdl_launch_count(b"tdl_photo_fwd") == 3
+    assert lib.tdl_launch_count(b"tdl_photo_fwd") == 4
 
 
 def test_ops_refuse_cpu_tensors(tdl):

@@ -89,6 +89,7 @@ int check_photo(const tdl_photo_args* a, bool bwd, PhotoDev* d) {
     d->argmin = reinterpret_cast<unsigned char*>(ws + L.argmin_off);
     d->automask = a->automask != 0;
     d->use_tma = getenv("TDL_NO_TMA") == nullptr;
+    d->split_fwd = getenv("TDL_FUSED_FWD") == nullptr;
     d->align_corners = a->align_corners != 0;
     d->min_disp = (float)(1.0 / a->max_depth);
     d->range = (float)(1.0 / a->min_depth - 1.0 / a->max_depth);
@@ -188,7 +189,7 @@ const char* tdl_strerror(int code) {
 
 int tdl_launch_count(const char* entry) {
     if (!entry) return 0;
-    if (!strcmp(entry, "tdl_photo_fwd")) return 3;        // photo_fwd, smooth_fwd, finalize
+    if (!strcmp(entry, "tdl_photo_fwd")) return 4;        // photo_warp + photo_score (or fused photo_fwd), smooth_fwd, finalize
     if (!strcmp(entry, "tdl_photo_bwd")) return 2;        // smooth_bwd, photo_bwd
     if (!strcmp(entry, "tdl_feat_fwd")) return 2;         // feat_fwd, finalize
     if (!strcmp(entry, "tdl_feat_bwd")) return 1;
@@ -244,7 +245,12 @@ int tdl_photo_fwd(const tdl_photo_args* a, tdl_stream_t stream) {
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("memset", cudaMemsetAsync(d.acc, 0, (size_t)a->nscales * a->B * 4 * sizeof(double), st));
-    TDL_KERNEL("photo_fwd", launch_photo_fwd(d, st));
+    if (photo_fwd_can_split(d)) {
+        TDL_KERNEL("photo_warp", launch_photo_warp(d, st));
+        TDL_KERNEL("photo_score", launch_photo_score(d, st));
+    } else {
+        TDL_KERNEL("photo_fwd", launch_photo_fwd(d, st));
+    }
     SmoothDev sm;
     photo_smooth_levels(a, d, false, &sm);
     TDL_KERNEL("smooth_fwd", launch_smooth_fwd(sm, st));

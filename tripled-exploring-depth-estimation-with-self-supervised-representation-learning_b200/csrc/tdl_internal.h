@@ -19,6 +19,7 @@ struct PhotoDev {
     float sy[TDL_MAX_SCALES], sx[TDL_MAX_SCALES];     // dh/H, dw/W (F.interpolate scale)
     int automask, align_corners;
     int use_tma;                 // stage image tiles with TMA box copies when the tensors allow it
+    int split_fwd;               // forward = warp kernel + TMA-staged scoring kernel (needs materialised warps)
     float min_disp, range;
     uint64_t seed;
     const float* target;
@@ -90,6 +91,9 @@ struct FeatDev {
 
 // launchers (each returns the cudaError_t of its launch)
 cudaError_t launch_photo_fwd(const PhotoDev& p, cudaStream_t st);
+bool photo_fwd_can_split(const PhotoDev& p);
+cudaError_t launch_photo_warp(const PhotoDev& p, cudaStream_t st);
+cudaError_t launch_photo_score(const PhotoDev& p, cudaStream_t st);
 cudaError_t launch_photo_bwd(const PhotoDev& p, cudaStream_t st);
 cudaError_t launch_smooth_fwd(const SmoothDev& p, cudaStream_t st);
 cudaError_t launch_smooth_bwd(const SmoothDev& p, cudaStream_t st);

@@ -330,6 +330,256 @@ __global__ void __launch_bounds__(kNT, 2) photo_fwd_kernel(const PhotoDev p) {
     }
 }
 
+
+// ================================================================================================
+// Split forward (used when the warped images are materialised and TMA can describe the tensors):
+//   photo_warp_kernel   one thread per pixel and scale: up-sample disp -> depth -> back-project -> project ->
+//                       bilinear border sampling of every source; writes outputs[("color", f, s)].  No halo,
+//                       no shared memory, high occupancy.
+//   photo_score_kernel  one CTA per 32x32 tile, all scales: stages the target, the sources (identity terms)
+//                       and, per scale, the S warped tiles with 3-D TMA box copies (halo 1, reflect cells
+//                       patched), then runs the SSIM + L1 + automask + min pipeline of photo_fwd_kernel.
+// Compared with the fused photo_fwd_kernel the projection is not recomputed for the tile halo, and the
+// scoring kernel carries no geometry code (fewer live registers, latency of the gathers hidden elsewhere).
+// ================================================================================================
+template <int S>
+__global__ void __launch_bounds__(256) photo_warp_kernel(const PhotoDev p) {
+    __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int H = p.H, W = p.W;
+    const size_t HW = (size_t)H * W;
+    if (tid < S * 12) s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
+    if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
+    __syncthreads();
+    const int pix = blockIdx.x * 256 + tid;
+    if (pix >= (int)HW) return;
+    const int y = pix / W, x = pix - y * W;
+    const DepthParams dp{p.min_disp, p.range};
+    // all scales of one pixel in one thread: the camera matrices are loaded once and the independent scales
+    // give the scheduler several gather rounds to overlap
+    float dsp[TDL_MAX_SCALES];
+#pragma unroll
+    for (int s = 0; s < TDL_MAX_SCALES; ++s) {
+        if (s < p.nscales) {
+            const int h = p.dh[s], w = p.dw[s];
+            const UpTap ut = up_tap(y, x, p.sy[s], p.sx[s], h, w);
+            dsp[s] = up_value(p.disp[s] + (size_t)b * h * w, w, ut);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < TDL_MAX_SCALES; ++s) {
+        if (s < p.nscales) {
+            const Geo g = backproject(dsp[s], dp, s_cam + TDL_MAX_SRC * 12, x, y);
+            Bilin bt[S];
+            float v[S][3][4];
+#pragma unroll
+            for (int f = 0; f < S; ++f) {
+                const Proj pr = project<false>(g, s_cam + f * 12, H, W, p.align_corners);
+                bt[f] = bilin_taps(pr.ix, pr.iy, H, W);
+                // block-uniform 64-bit base + 32-bit per-thread offsets: one integer add per access
+                const float* sb = p.src[f] + (size_t)b * 3 * HW;
+                const unsigned o00 = (unsigned)(bt[f].y0 * W + bt[f].x0);
+                const unsigned o01 = o00 + (bt[f].vx ? 1u : 0u), o10 = o00 + (bt[f].vy ? (unsigned)W : 0u);
+                const unsigned o11 = o10 + (bt[f].vx ? 1u : 0u);
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const unsigned co = (unsigned)ch * (unsigned)HW;
+                    v[f][ch][0] = __ldg(sb + (co + o00));
+                    v[f][ch][1] = __ldg(sb + (co + o01));
+                    v[f][ch][2] = __ldg(sb + (co + o10));
+                    v[f][ch][3] = __ldg(sb + (co + o11));
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < S; ++f) {
+                float* wo = p.warped[s][f] + (size_t)b * 3 * HW;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    float acc = v[f][ch][0] * bt[f].nw;
+                    acc += v[f][ch][1] * bt[f].ne;
+                    acc += v[f][ch][2] * bt[f].sw;
+                    acc += v[f][ch][3] * bt[f].se;
+                    wo[(unsigned)ch * (unsigned)HW + (unsigned)pix] = acc;
+                }
+            }
+        }
+    }
+}
+
+constexpr int kFX0 = 4, kFY0 = 1;                       // tile origin inside the staged forward box
+constexpr int kFW = kTW + 8, kFH = kTH + 2, kFPLANE = kFW * kFH;
+constexpr int kFGROUP = (3 * kFPLANE + 31) / 32 * 32;   // 3 planes, 128-byte multiple (TMA destination)
+
+// patch the reflect cells (one pixel outside the image) of `ngroups` staged 3-plane groups
+TDL_DEV void reflect_fix(float* groups, int ngroups, int tx0, int ty0, int H, int W, int tid) {
+    const bool bl = tx0 == 0, br = tx0 + kTW >= W, bt_ = ty0 == 0, bb = ty0 + kTH >= H;
+    if (bl || br) {
+        for (int e = tid; e < ngroups * 3 * kFH; e += kNT) {
+            const int g = e / (3 * kFH), rem = e - g * 3 * kFH, ch = rem / kFH, r = rem - ch * kFH;
+            float* row = groups + g * kFGROUP + ch * kFPLANE + r * kFW;
+            if (bl) row[kFX0 - 1] = row[kFX0 + 1];
+            if (br) row[W - tx0 + kFX0] = row[W - tx0 + kFX0 - 2];
+        }
+    }
+    if (bt_ || bb) {
+        __syncthreads();
+        for (int e = tid; e < ngroups * 3 * kFW; e += kNT) {
+            const int g = e / (3 * kFW), rem = e - g * 3 * kFW, ch = rem / kFW, c = rem - ch * kFW;
+            float* col = groups + g * kFGROUP + ch * kFPLANE + c;
+            if (bt_) col[(kFY0 - 1) * kFW] = col[(kFY0 + 1) * kFW];
+            if (bb) col[(H - ty0 + kFY0) * kFW] = col[(H - ty0 + kFY0 - 2) * kFW];
+        }
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(kNT, 2) photo_score_kernel(const PhotoDev p, const __grid_constant__ PhotoMaps maps,
+                                                           const __grid_constant__ PhotoMaps wmaps) {
+    constexpr int FW = kFW, FPLANE = kFPLANE, FGROUP = kFGROUP;
+    extern __shared__ __align__(128) float smem_score[];
+    float* s_tgt = smem_score;                 // group 0: target
+    float* s_img = smem_score + FGROUP;        // groups 1..S: sources (identity terms), then warped per scale
+    __shared__ float s_red[32];
+    __shared__ uint64_t s_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int b = blockIdx.z, tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
+    const int H = p.H, W = p.W;
+    const size_t HW = (size_t)H * W;
+    constexpr uint32_t kGroupBytes = 3 * FPLANE * sizeof(float);
+
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&s_bar, (1 + S) * kGroupBytes);
+        tma_load_3d(s_tgt, &maps.tgt, &s_bar, tx0 - kFX0, ty0 - kFY0, b * 3);
+#pragma unroll
+        for (int f = 0; f < S; ++f) tma_load_3d(s_img + f * FGROUP, &maps.img[f], &s_bar, tx0 - kFX0, ty0 - kFY0, b * 3);
+    }
+    uint32_t parity = 0;
+    mbar_wait(&s_bar, parity);
+    parity ^= 1;
+    reflect_fix(smem_score, 1 + S, tx0, ty0, H, W, tid);
+    __syncthreads();
+
+    // ---- area-downsampled target pyramid (F.interpolate(mode='area'), net.py:259) and disparity sums
+    for (int s = 0; s < p.nscales; ++s) {
+        const int fac = p.fac[s], cells = kTW / fac, h = p.dh[s], w = p.dw[s];
+        const int cj0 = ty0 / fac, ci0 = tx0 / fac;
+        const float inv = 1.f / (float)(fac * fac);
+        float dsum = 0.f;
+        for (int i = tid; i < cells * cells * 3; i += kNT) {
+            const int ch = i / (cells * cells), rem = i - ch * cells * cells;
+            const int cj = rem / cells, ci = rem - cj * cells;
+            if (cj0 + cj < h && ci0 + ci < w) {
+                const float* base = s_tgt + ch * FPLANE + (kFY0 + cj * fac) * FW + kFX0 + ci * fac;
+                float acc = 0.f;
+                for (int dy = 0; dy < fac; ++dy)
+                    for (int dx = 0; dx < fac; ++dx) acc += base[dy * FW + dx];
+                const size_t o = (((size_t)b * 3 + ch) * h + cj0 + cj) * w + ci0 + ci;
+                p.J[s][o] = acc * inv;
+                if (ch == 0) dsum += __ldg(p.disp[s] + ((size_t)b * h + cj0 + cj) * w + ci0 + ci);
+            }
+        }
+        dsum = block_sum(dsum, s_red);
+        if (tid == 0) atomicAdd(p.acc + ((size_t)s * p.B + b) * 4 + 1, (double)dsum);
+    }
+
+    // ---- per-thread strip: column `lane`, rows wrp*kR .. of the tile; window corner (r0, lane + kFX0 - 1)
+    const int r0 = wrp * kR, c0 = lane + kFX0 - 1;
+    const int gx = tx0 + lane;
+    float* s_stats = s_img + S * FGROUP + tid;      // [ch][mu|sigma][i][thread]
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float mu_y[kR], sg_y[kR];
+        strip_target_stats<FW>(s_tgt + ch * FPLANE, r0, c0, mu_y, sg_y);
+#pragma unroll
+        for (int i = 0; i < kR; ++i) {
+            s_stats[((ch * 2) * kR + i) * kNT] = mu_y[i];
+            s_stats[((ch * 2 + 1) * kR + i) * kNT] = sg_y[i];
+        }
+    }
+    float rho_id[S][kR];
+    if (p.automask) {
+#pragma unroll
+        for (int f = 0; f < S; ++f)
+            strip_reprojection<FW>(s_img + f * FGROUP, s_tgt, FPLANE, r0, c0, s_stats, rho_id[f]);
+    }
+    __syncthreads();
+
+    for (int s = 0; s < p.nscales; ++s) {
+        // ---- stage the S warped tiles of this scale (written by photo_warp_kernel)
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(&s_bar, S * kGroupBytes);
+#pragma unroll
+            for (int f = 0; f < S; ++f)
+                tma_load_3d(s_img + f * FGROUP, &wmaps.img[s * S + f], &s_bar, tx0 - kFX0, ty0 - kFY0, b * 3);
+        }
+        mbar_wait(&s_bar, parity);
+        parity ^= 1;
+        reflect_fix(s_img, S, tx0, ty0, H, W, tid);
+        __syncthreads();
+
+        // ---- reprojection errors, automask, minimum over frames
+        float best[kR];
+        int arg[kR];
+#pragma unroll
+        for (int i = 0; i < kR; ++i) {
+            best[i] = 0.f;
+            arg[i] = -1;
+        }
+        int chan = 0;
+        if (p.automask) {
+#pragma unroll
+            for (int i = 0; i < kR; ++i) {
+                const int gy = ty0 + r0 + i;
+                float nz[S];
+#pragma unroll
+                for (int f = 0; f < S; ++f) nz[f] = 0.f;
+                if (gx < W && gy < H) automask_noise<S>(p, s, b, (size_t)gy * W + gx, HW, nz);
+#pragma unroll
+                for (int f = 0; f < S; ++f) {
+                    const float v = __fadd_rn(rho_id[f][i], __fmul_rn(nz[f], 1e-5f));     // net.py:94
+                    if (f == 0 || v < best[i]) {
+                        best[i] = v;
+                        arg[i] = f;
+                    }
+                }
+            }
+            chan = S;
+        }
+#pragma unroll
+        for (int f = 0; f < S; ++f) {
+            float rho[kR];
+            strip_reprojection<FW>(s_img + f * FGROUP, s_tgt, FPLANE, r0, c0, s_stats, rho);
+#pragma unroll
+            for (int i = 0; i < kR; ++i) {
+                if (arg[i] < 0 || rho[i] < best[i]) {
+                    best[i] = rho[i];
+                    arg[i] = chan;
+                }
+            }
+            ++chan;
+        }
+        float lsum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kR; ++i) {
+            const int gy = ty0 + r0 + i;
+            if (gx < W && gy < H) {
+                const size_t pix = (size_t)gy * W + gx;
+                lsum += best[i];
+                p.argmin[((size_t)s * p.B + b) * HW + pix] = (unsigned char)arg[i];
+                if (p.min_index[s]) p.min_index[s][(size_t)b * HW + pix] = arg[i];
+            }
+        }
+        lsum = block_sum(lsum, s_red);
+        if (tid == 0) atomicAdd(p.acc + ((size_t)s * p.B + b) * 4 + 0, (double)lsum);
+        __syncthreads();           // every thread is done with s_img before the next scale's TMA overwrites it
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Backward.
 // Backward tile: halo 2 in y, and in x a left margin of 4 so that the TMA box starts on a 16-byte boundary
@@ -722,7 +972,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
 
 // ------------------------------------------------------------------------------------------------
 template <int S>
-static cudaError_t launch_fwd_t(const PhotoDev& p, cudaStream_t st) {
+static cudaError_t launch_fwd_fused(const PhotoDev& p, cudaStream_t st) {
     constexpr int PLANE = (kTW + 2) * (kTH + 2);
     const size_t smem = (size_t)(3 + 3 * S) * PLANE * sizeof(float) + (size_t)6 * kR * kNT * sizeof(float);
     static bool attr_done = false;
@@ -734,6 +984,69 @@ static cudaError_t launch_fwd_t(const PhotoDev& p, cudaStream_t st) {
     dim3 grid((p.W + kTW - 1) / kTW, (p.H + kTH - 1) / kTH, p.B);
     photo_fwd_kernel<S><<<grid, kNT, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int S>
+static bool encode_fwd_maps(const PhotoDev& p, PhotoMaps* maps, PhotoMaps* wmaps) {
+    // split path: every warped image is materialised and TMA can describe target / sources / warps
+    bool ok = p.use_tma && p.split_fwd && encode_image_map(&maps->tgt, p.target, p.B * 3, p.H, p.W, kFW, kFH, 3);
+    for (int f = 0; ok && f < S; ++f) ok = encode_image_map(&maps->img[f], p.src[f], p.B * 3, p.H, p.W, kFW, kFH, 3);
+    for (int s = 0; ok && s < p.nscales; ++s)
+        for (int f = 0; ok && f < S; ++f)
+            ok = p.warped[s][f] && encode_image_map(&wmaps->img[s * S + f], p.warped[s][f], p.B * 3, p.H, p.W, kFW, kFH, 3);
+    return ok;
+}
+
+template <int S>
+static cudaError_t launch_warp_t(const PhotoDev& p, cudaStream_t st) {
+    dim3 wgrid((unsigned)(((size_t)p.H * p.W + 255) / 256), p.B);
+    photo_warp_kernel<S><<<wgrid, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int S>
+static cudaError_t launch_score_t(const PhotoDev& p, cudaStream_t st) {
+    PhotoMaps maps, wmaps;
+    if (!encode_fwd_maps<S>(p, &maps, &wmaps)) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)(1 + S) * kFGROUP * sizeof(float) + (size_t)6 * kR * kNT * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(photo_score_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((p.W + kTW - 1) / kTW, (p.H + kTH - 1) / kTH, p.B);
+    photo_score_kernel<S><<<grid, kNT, smem, st>>>(p, maps, wmaps);
+    return cudaGetLastError();
+}
+
+#define TDL_DISPATCH_S(fn, ...)                  \
+    switch (p.S) {                               \
+        case 1: return fn<1>(__VA_ARGS__);       \
+        case 2: return fn<2>(__VA_ARGS__);       \
+        case 3: return fn<3>(__VA_ARGS__);       \
+        case 4: return fn<4>(__VA_ARGS__);       \
+    }
+
+bool photo_fwd_can_split(const PhotoDev& p) {
+    PhotoMaps maps, wmaps;
+    switch (p.S) {
+        case 1: return encode_fwd_maps<1>(p, &maps, &wmaps);
+        case 2: return encode_fwd_maps<2>(p, &maps, &wmaps);
+        case 3: return encode_fwd_maps<3>(p, &maps, &wmaps);
+        case 4: return encode_fwd_maps<4>(p, &maps, &wmaps);
+    }
+    return false;
+}
+
+cudaError_t launch_photo_warp(const PhotoDev& p, cudaStream_t st) {
+    TDL_DISPATCH_S(launch_warp_t, p, st)
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_photo_score(const PhotoDev& p, cudaStream_t st) {
+    TDL_DISPATCH_S(launch_score_t, p, st)
+    return cudaErrorInvalidValue;
 }
 
 template <int S, bool kTMA>
@@ -761,13 +1074,8 @@ static cudaError_t launch_bwd_t(const PhotoDev& p, cudaStream_t st) {
     return tma ? launch_bwd_k<S, true>(p, maps, st) : launch_bwd_k<S, false>(p, maps, st);
 }
 
-cudaError_t launch_photo_fwd(const PhotoDev& p, cudaStream_t st) {
-    switch (p.S) {
-        case 1: return launch_fwd_t<1>(p, st);
-        case 2: return launch_fwd_t<2>(p, st);
-        case 3: return launch_fwd_t<3>(p, st);
-        case 4: return launch_fwd_t<4>(p, st);
-    }
+cudaError_t launch_photo_fwd(const PhotoDev& p, cudaStream_t st) {       // fused single-kernel forward
+    TDL_DISPATCH_S(launch_fwd_fused, p, st)
     return cudaErrorInvalidValue;
 }
 
