@@ -636,6 +636,17 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     const float* db = p.disp[s] + (size_t)b * h * w;
     const unsigned char* am = p.argmin + ((size_t)s * p.B + b) * HW;
 
+    // depth / ray / camera point of this thread's pixels: independent of the source frame AND of the staged
+    // tiles, so it is computed here, while the TMA copies issued above are in flight
+    const int r0 = wrp * kR;
+    const int gx = tx0 + lane;
+    Geo geo[kR];
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+        const UpTap ut{s_ty0[r0 + i], s_ty1[r0 + i], s_tx0[lane], s_tx1[lane], s_tly[r0 + i], s_tlx[lane]};
+        geo[i] = backproject(up_value(db, w, ut), dp, s_iK, gx, ty0 + r0 + i);
+    }
+
     // ---- phase 1: target, argmin mask and the warped sources over the tile with halo 2.  When the forward
     //      materialised outputs[("color",f,s)] they are re-read (coalesced, bit-identical to what the forward
     //      scored); otherwise the warp is recomputed.  All loads of a thread are issued before the first
@@ -730,19 +741,10 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     }
     __syncthreads();
 
-    const int r0 = wrp * kR;
-    const int gx = tx0 + lane;
     float gd[kR];                       // d loss / d (up-sampled disparity) of this thread's pixels
 #pragma unroll
     for (int i = 0; i < kR; ++i) gd[i] = 0.f;
     const float g_ssim = up * 0.85f / 3.f, g_l1 = up * 0.15f / 3.f;
-    // depth / ray / camera point of this thread's pixels do not depend on the source frame
-    Geo geo[kR];
-#pragma unroll
-    for (int i = 0; i < kR; ++i) {
-        const UpTap ut{s_ty0[r0 + i], s_ty1[r0 + i], s_tx0[lane], s_tx1[lane], s_tly[r0 + i], s_tlx[lane]};
-        geo[i] = backproject(up_value(db, w, ut), dp, s_iK, gx, ty0 + r0 + i);
-    }
 
 #pragma unroll 1
     for (int f = 0; f < S; ++f) {
