@@ -359,6 +359,37 @@ def train_step_bench(args, device, rank, world, dist_on):
             "final_loss": float(loss.detach())}
 
 
+def time_eager_gpu_port(B, H, W, device, steps=5, warmup=2):
+    """The reference's loss as stock eager PyTorch ops on this same GPU (the oracle port run on CUDA tensors,
+    ~150-200 kernel launches per scale): a reported baseline for the fused kernels, like the CPU port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import run_restatement
+    rec = cpu_record(B, H, W, 4321)
+    rec = {"inputs": {k: v.to(device) for k, v in rec["inputs"].items()},
+           "leaves": {k: v.to(device) for k, v in rec["leaves"].items()}, "meta": rec["meta"]}
+    import oracle.restatement as R
+    draw = R.draw_automask_noise
+
+    def draw_dev(spec, batch, generator=None, dtype=torch.float32):       # the reference: CPU randn + .cuda()
+        return {s: {f: n.to(device) for f, n in d.items()} for s, d in draw(spec, batch, generator, dtype).items()}
+    R.draw_automask_noise = draw_dev
+    try:
+        def one():
+            loss, _, _ = run_restatement(rec)
+            sum(loss.values()).backward()
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        torch.cuda.synchronize(device)
+        dt = (time.perf_counter() - t0) / steps
+    finally:
+        R.draw_automask_noise = draw
+    return B / dt, dt
+
+
 def config_dict(args, trainable):
     return {"workload": f"mono_fm loss fwd+bwd (cfg_kitti_fm): {args.height}x{args.width}, batch {args.batch}/GPU, "
                         f"frames [0,-1,1], 4 scales, {FEAT_C}-ch features at H/2xW/2, "
@@ -549,6 +580,16 @@ def run():
                "sample": f"batch {args.cpu_batch} of the same {H}x{W} workload, 8 timed steps after 1 warm-up "
                          f"({spstep:.2f} s/step), oracle/restatement.py on all host threads"}
 
+    eager = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            ips, spstep = time_eager_gpu_port(B, H, W, device)
+            eager = {"value": round(ips, 1), "unit": "images/s", "ms_per_step": round(spstep * 1e3, 2), "kind": "port",
+                     "what": "the reference's loss op sequence (oracle/restatement.py) as eager PyTorch on this GPU, "
+                             f"batch {B}, host-timed with synchronisation, 5 steps after 2 warm-ups"}
+        except Exception as exc:                       # pragma: no cover - baseline only
+            eager = {"unavailable": f"{type(exc).__name__}: {exc}"}
+
     line = {"metric": "fused_loss_fwd_bwd_images_per_s", "value": round(value, 1), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -557,7 +598,8 @@ def run():
                     "d2h_bytes_per_step": step.losses_host.numel() * 4, "ms_per_step": round(ms_e2e / e2e_steps, 4),
                     "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "train_step": train}
+            "roofline": roofline, "cpu_baseline": cpu, "eager_torch_gpu_baseline": eager,
+            "train_step": train}
     if dist_on:
         torch.distributed.destroy_process_group()
     return line

@@ -53,21 +53,22 @@ def disp_to_depth(disp, min_depth, max_depth):
     return scaled, 1 / scaled
 
 
-def pixel_grid(batch, height, width, dtype=torch.float32):
+def pixel_grid(batch, height, width, dtype=torch.float32, device=None):
     """Homogeneous pixel coordinates (B,3,H*W): rows x, y, 1.
-    mono/model/mono_fm/layers.py:49-55."""
-    ys, xs = torch.meshgrid(torch.arange(height, dtype=dtype),
-                            torch.arange(width, dtype=dtype), indexing="ij")
-    pix = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(height * width, dtype=dtype)], 0)
+    mono/model/mono_fm/layers.py:49-55 (the reference builds them on the host and calls .cuda() per use;
+    ``device`` lets bench.py time this same op sequence as eager PyTorch on the GPU)."""
+    ys, xs = torch.meshgrid(torch.arange(height, dtype=dtype, device=device),
+                            torch.arange(width, dtype=dtype, device=device), indexing="ij")
+    pix = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(height * width, dtype=dtype, device=device)], 0)
     return pix.unsqueeze(0).repeat(batch, 1, 1)
 
 
 def backproject(depth, inv_K):
     """mono/model/mono_fm/layers.py:57-61."""
     b, _, h, w = depth.shape
-    rays = torch.matmul(inv_K[:, :3, :3], pixel_grid(b, h, w, depth.dtype))
+    rays = torch.matmul(inv_K[:, :3, :3], pixel_grid(b, h, w, depth.dtype, depth.device))
     cam = depth.view(b, 1, -1) * rays
-    return torch.cat([cam, torch.ones(b, 1, h * w, dtype=depth.dtype)], 1)
+    return torch.cat([cam, torch.ones(b, 1, h * w, dtype=depth.dtype, device=depth.device)], 1)
 
 
 def project(cam_points, K, T, height, width, eps=1e-7):
