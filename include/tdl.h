@@ -26,6 +26,8 @@
  *                                       mono/model/mono_fm_joint_inpaint/net.py:58-70
  *   tdl_edge_smooth_fwd / tdl_edge_smooth_bwd
  *       get_feature_regularization_loss mono/model/mono_fm_joint/net.py:309-330
+ *   tdl_recon_fwd / tdl_recon_bwd
+ *       masked img_reconstruct_loss     mono/model/mono_fm_joint_inpaint/net.py:80-91
  *
  * Conventions
  *   - every tensor is fp32, NCHW, contiguous, resident in device memory; only
@@ -151,6 +153,21 @@ typedef struct tdl_kernel_time {
     double total_ms;
 } tdl_kernel_time;
 
+/* ------------------------------------------------------------------ masked image reconstruction (TripleD) */
+typedef struct tdl_recon_args {
+    int32_t B, h, w;            /* pred / target / mask are (B,3,h,w)                                    */
+    float coef;                 /* loss = coef * sum(rho * (1 - mask)) / sum(1 - mask),
+                                   rho = 0.85 mean_c SSIM(pred,target) + 0.15 mean_c robust_l1 (B,1,h,w) */
+    const float* pred;          /* outputs[("res_img",0,s)]                                              */
+    const float* target;        /* target resized to (h,w) (F.interpolate bilinear, done by the caller)  */
+    const float* mask;          /* mask resized to (h,w); NULL => plain mean                             */
+    void* workspace;
+    uint64_t workspace_bytes;
+    float* loss;                /* out [1] */
+    const float* dloss;         /* [1], backward only */
+    float* d_pred;              /* out (B,3,h,w), overwritten, backward only */
+} tdl_recon_args;
+
 int tdl_abi_version(void);
 const char* tdl_strerror(int code);
 /* number of CUDA kernels (not memsets) one call launches -- used by bench.py's gpu_launches */
@@ -173,6 +190,10 @@ int tdl_feat_bwd(const tdl_feat_args* args, tdl_stream_t stream);
 uint64_t tdl_edge_ws_bytes(int32_t B, int32_t C, int32_t h, int32_t w);
 int tdl_edge_smooth_fwd(const tdl_edge_args* args, tdl_stream_t stream);
 int tdl_edge_smooth_bwd(const tdl_edge_args* args, tdl_stream_t stream);
+
+uint64_t tdl_recon_ws_bytes(void);
+int tdl_recon_fwd(const tdl_recon_args* args, tdl_stream_t stream);
+int tdl_recon_bwd(const tdl_recon_args* args, tdl_stream_t stream);
 
 #ifdef __cplusplus
 }

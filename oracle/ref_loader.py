@@ -125,7 +125,8 @@ def make_loss_only_net(kind, opt):
 
     kind: 'baseline' (mono/model/mono_baseline/net.py:51-100),
           'fm'       (mono/model/mono_fm/net.py:69-133),
-          'inpaint'  (mono/model/mono_fm_joint_inpaint/net.py:47-133).
+          'inpaint'  (mono/model/mono_fm_joint_inpaint/net.py:47-133),
+          'tripled'  (mono/model/mono_fm_joint_inpaint/net.py:398-532, adds auto_res_loss).
     """
     mods = load()
     L = mods["layers"]
@@ -135,6 +136,8 @@ def make_loss_only_net(kind, opt):
         cls = mods["fm"].mono_fm
     elif kind == "inpaint":
         cls = mods["inpaint"].mono_fm_joint_inpaint
+    elif kind == "tripled":                      # the TripleD net of config/cfg_kitti_tripleD.py
+        cls = mods["inpaint"].mono_fm_joint_inpaint_disentangle
     else:
         raise ValueError(kind)
     net = cls.__new__(cls)
@@ -147,6 +150,6 @@ def make_loss_only_net(kind, opt):
     net.project_3d = proj
     if kind == "fm":
         net.extractor = _Feat()
-    if kind == "inpaint":
+    if kind in ("inpaint", "tripled"):
         net.Encoder = _Feat()
     return net

@@ -307,6 +307,24 @@ def compute_losses_inpaint_core(spec: LossSpec, inputs, outputs, noise, tgt_feat
     return loss
 
 
+def img_reconstruct_loss(spec: LossSpec, inputs, outputs, scale, weight=1):
+    """mono/model/mono_fm_joint_inpaint/net.py:80-91: SSIM + L1 of the autoencoder output against the
+    bilinearly resized target, averaged over the erased (mask == 0) region."""
+    target, mask = inputs[("color", 0, 0)], inputs[("mask", 0, 0)]
+    res_img = outputs[("res_img", 0, scale)]
+    _, _, h, w = res_img.size()
+    target_resize = F.interpolate(target, [h, w], mode="bilinear", align_corners=False)
+    mask_resize = F.interpolate(mask, [h, w], mode="bilinear", align_corners=False)
+    loss = reprojection_loss(res_img, target_resize)
+    loss = torch.sum(loss * (1 - mask_resize)) / torch.sum(1 - mask_resize)
+    return loss / len(spec.scales) * weight
+
+
+def auto_res_loss(inputs, outputs, weight):
+    """mono/model/mono_fm_joint_inpaint/net.py:520-527 (un-reduced (B,1,H,W) map, as in the reference)."""
+    return perceptional_loss(inputs[("color", 0, 0)], outputs[("auto_res_img", 0, 0)]) * weight
+
+
 def feature_regularization_loss(feature, img, dis, cvt):
     """mono/model/mono_fm_joint/net.py:309-330 (exponent coefficient 1,
     ``-dis * first + cvt * second``)."""

@@ -27,6 +27,8 @@ CASES = {
     "baseline_waves_b2_64x96": ("baseline", 2, 64, 96, "waves", 0, 1234),
     "fm_waves_b2_64x96_c8": ("fm", 2, 64, 96, "waves", 8, 1236),
     "inpaint_waves_b1_96x128_c8": ("inpaint", 1, 96, 128, "waves", 8, 1237),
+    # TripleD net (cfg_kitti_tripleD): + masked autoencoder reconstruction (16 erased 8x8 holes) + auto_res_loss
+    "tripled_waves_b1_96x128_c8": ("tripled", 1, 96, 128, "waves", 8, 1238),
     # "smooth": box-filtered noise frames -- realistic, judged with the kink-robust metric
     "baseline_smooth_b2_64x96": ("baseline", 2, 64, 96, "smooth", 0, 1234),
     # 32x64: disp_3 is 2x4, so d_dyy is empty and the reference's smooth_loss is NaN
@@ -36,7 +38,8 @@ CASES = {
 
 
 def run_reference(kind, B, H, W, frames, C, seed):
-    opt = ref_loader.default_opt(B, H, W, dis=1e-3, cvt=1e-3, img_reconstruct_weight=0)
+    opt = ref_loader.default_opt(B, H, W, dis=1e-3, cvt=1e-3, img_reconstruct_weight=1 if kind == "tripled" else 0,
+                                 auto_res_weight=5e-3)
     inputs, outputs, extras = synth.make_inputs(B, H, W, seed=seed, frames=frames,
                                                 feat_channels=C, with_noise=False)
     leaves = {}
@@ -55,7 +58,7 @@ def run_reference(kind, B, H, W, frames, C, seed):
             table[inputs[("color", f, 0)].data_ptr()] = t
         table[inputs[("color", 0, 0)].data_ptr()] = tgt
         (net.extractor if kind == "fm" else net.Encoder).table = table
-        if kind == "inpaint":
+        if kind in ("inpaint", "tripled"):
             # 5 feature levels; only level 0 enters the view-synthesis path, the
             # others feed get_feature_regularization_loss.
             g = torch.Generator().manual_seed(seed + 99)
@@ -64,14 +67,28 @@ def run_reference(kind, B, H, W, frames, C, seed):
                 f_i = torch.randn(B, 4, H >> (i + 1), W >> (i + 1), generator=g).requires_grad_(True)
                 leaves[("feat_level", i)] = f_i
                 features.append(f_i)
-            inputs[("mask", 0, 0)] = torch.ones(B, 3, H, W)
+            mask = torch.ones(B, 3, H, W)
+            if kind == "tripled":                  # erase mask (mono/datasets/kitti_dataset.py:167-182) + decoder outputs
+                for _ in range(16):
+                    y0 = int(torch.randint(0, H - 8, (1,), generator=g))
+                    x0 = int(torch.randint(0, W - 8, (1,), generator=g))
+                    mask[:, :, y0:y0 + 8, x0:x0 + 8] = 0
+                for s in range(4):
+                    r = torch.sigmoid(torch.nn.functional.avg_pool2d(
+                        torch.randn(B, 3, (H >> s) + 4, (W >> s) + 4, generator=g), 5, 1) * 2).requires_grad_(True)
+                    leaves[("res_img", 0, s)] = r
+                    outputs[("res_img", 0, s)] = r
+                a = (inputs[("color", 0, 0)] + 0.05 * torch.randn(B, 3, H, W, generator=g)).clamp(0, 1).requires_grad_(True)
+                leaves[("auto_res_img", 0, 0)] = a
+                outputs[("auto_res_img", 0, 0)] = a
+            inputs[("mask", 0, 0)] = mask
     torch.manual_seed(seed)          # the reference draws automask noise from the global CPU RNG
     with ref_loader.cpu_cuda_shim():
-        if kind == "inpaint":
+        if kind in ("inpaint", "tripled"):
             loss_dict = net.compute_losses(inputs, outputs, features)
         else:
             loss_dict = net.compute_losses(inputs, outputs)
-    total = sum(v for v in loss_dict.values())
+    total = sum(v.mean() for v in loss_dict.values())      # batch_processor: .mean() of every entry (trainer.py:39-48)
     total.backward()
     rec = {
         "inputs": {k: v.detach().clone() for k, v in inputs.items()},
@@ -93,7 +110,7 @@ def main():
         path = os.path.join(HERE, name + ".pt")
         torch.save(rec, path)
         print(name, os.path.getsize(path) // 1024, "KiB",
-              {str(k): float(v) for k, v in rec["loss"].items()})
+              {str(k): float(v.mean()) for k, v in rec["loss"].items()})
 
 
 if __name__ == "__main__":

@@ -36,7 +36,8 @@ def run_restatement(rec, dtype=torch.float32, forced=None):
     spec = spec_from_meta(meta)
     inputs = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in rec["inputs"].items()}
     leaves = {k: v.to(dtype).clone().requires_grad_(True) for k, v in rec["leaves"].items()}
-    outputs = {k: v for k, v in leaves.items() if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam")}
+    outputs = {k: v for k, v in leaves.items()
+               if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam", "res_img", "auto_res_img")}
     noise = reference_noise(spec, meta)
     noise = {s: {f: n.to(dtype) for f, n in d.items()} for s, d in noise.items()}
     kind = meta["kind"]
@@ -52,6 +53,11 @@ def run_restatement(rec, dtype=torch.float32, forced=None):
             for i, f in enumerate(feats):
                 loss[("feature_regularization_loss", i)] = R.feature_regularization_loss(
                     f, inputs[("color", 0, 0)], spec.extra["dis"], spec.extra["cvt"]) / (2 ** i) / 5
+            if kind == "tripled":
+                for sc in spec.scales:
+                    loss[("img_reconstruct_loss", sc)] = R.img_reconstruct_loss(spec, inputs, outputs, sc)
             loss.update(R.compute_losses_inpaint_core(spec, inputs, outputs, noise, leaves["tgt_feat"], src,
                                                        forced=forced))
+            if kind == "tripled":
+                loss["auto_res_loss"] = R.auto_res_loss(inputs, outputs, spec.extra["auto_res_weight"])
     return loss, outputs, leaves

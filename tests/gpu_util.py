@@ -36,7 +36,8 @@ def run_cuda(rec, noise, dev="cuda", kind=None):
     net = make_loss_net(meta["opt"], kind)
     inputs = {k: v.to(dev) for k, v in rec["inputs"].items()}
     leaves = {k: v.to(dev).clone().requires_grad_(True) for k, v in rec["leaves"].items()}
-    outputs = {k: v for k, v in leaves.items() if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam")}
+    outputs = {k: v for k, v in leaves.items()
+               if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam", "res_img", "auto_res_img")}
     noise_d = {s: {f: n.to(dev) for f, n in d.items()} for s, d in noise.items()}
     frames = meta["opt"]["frame_ids"][1:]
     if kind == "baseline":
@@ -48,7 +49,9 @@ def run_cuda(rec, noise, dev="cuda", kind=None):
         else:
             feats = [leaves["tgt_feat"]] + [leaves[("feat_level", i)] for i in range(1, 5)]
             loss = net.compute_losses_joint_core(inputs, outputs, feats, noise_d, src)
-    total = sum(loss.values())
+            if kind == "tripled":
+                loss.update(net.compute_auto_res_loss(inputs, outputs))
+    total = sum(v.mean() for v in loss.values())
     total.backward()
     torch.cuda.synchronize()
     grads = {k: (v.grad.detach().cpu() if v.grad is not None else None) for k, v in leaves.items()}

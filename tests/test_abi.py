@@ -27,7 +27,7 @@ def declared_functions():
 
 def test_exports_every_declared_symbol(lib, tdl):
     names = declared_functions()
-    assert len(names) >= 14
+    assert len(names) >= 17
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/tdl.h but not exported by libtdl.so"
     assert sorted(tdl._lib.EXPORTS) == names
@@ -47,6 +47,7 @@ int main(void) {
          offsetof(tdl_photo_args, noise), offsetof(tdl_photo_args, losses), offsetof(tdl_photo_args, dP));
   printf("%zu %zu %zu\\n", offsetof(tdl_feat_args, tgt), offsetof(tdl_feat_args, loss), offsetof(tdl_feat_args, dP));
   printf("%zu %zu\\n", offsetof(tdl_edge_args, feature), offsetof(tdl_edge_args, d_feature));
+  printf("%zu %zu %zu\\n", sizeof(tdl_recon_args), offsetof(tdl_recon_args, pred), offsetof(tdl_recon_args, d_pred));
   return 0; }''')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
@@ -61,6 +62,8 @@ int main(void) {
     assert list(map(int, out[2].split())) == [F.tgt.offset, F.loss.offset, F.dP.offset]
     E = L.EdgeArgs
     assert list(map(int, out[3].split())) == [E.feature.offset, E.d_feature.offset]
+    Rc = L.ReconArgs
+    assert list(map(int, out[4].split())) == [C.sizeof(Rc), Rc.pred.offset, Rc.d_pred.offset]
 
 
 def test_argument_errors_without_a_gpu(lib, tdl):

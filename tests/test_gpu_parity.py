@@ -92,11 +92,14 @@ def _check(rec, tag, golden=None, img_rtol=IMG_RTOL, grad_rtol=GRAD_RTOL, flip_b
             flips_total += n
     if forced:      # gradients are compared under OUR selection (see module docstring)
         ref_loss, ref_out, ref_leaves = run_restatement(rec, forced=forced)
-    sum(ref_loss.values()).backward()
+    sum(v.mean() for v in ref_loss.values()).backward()
 
     # ---- loss scalars and warped images / features
     for k, v in ref_loss.items():
         v = v.detach()
+        if v.dim():                                      # un-reduced map (auto_res_loss): compare as a tensor
+            assert rel_l2(loss[k], v) <= img_rtol, f"{tag} loss map {k}"
+            continue
         if torch.isnan(v):
             assert torch.isnan(loss[k]), f"{tag} {k}: reference is NaN (empty difference map), got {loss[k]}"
             continue
@@ -127,7 +130,7 @@ def _check(rec, tag, golden=None, img_rtol=IMG_RTOL, grad_rtol=GRAD_RTOL, flip_b
     # ---- the golden vectors themselves (produced by the real reference)
     if golden is not None:
         for k, v in golden["loss"].items():
-            if not torch.isnan(v):
+            if v.dim() == 0 and not torch.isnan(v):
                 assert _scalar_err(loss[k], v) <= loss_rtol, f"{tag} golden loss {k}"
         for k, v in golden["out"].items():
             if v.dtype.is_floating_point:

@@ -20,7 +20,7 @@ def test_restatement_matches_reference_golden(name):
         if got.dtype == torch.int64:
             got = got.to(torch.uint8)
         torch.testing.assert_close(got, v, rtol=0, atol=0, msg=str(k))
-    sum(loss.values()).backward()     # a NaN term (empty difference map) still back-props its finite parts
+    sum(v.mean() for v in loss.values()).backward()     # a NaN term (empty difference map) still back-props its finite parts
     for k, g in rec["grad"].items():
         if g is None:
             assert leaves[k].grad is None or leaves[k].grad.abs().max() == 0

@@ -60,6 +60,15 @@ class EdgeArgs(C.Structure):
     ]
 
 
+class ReconArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("coef", C.c_float),
+        ("pred", _vp), ("target", _vp), ("mask", _vp),
+        ("workspace", _vp), ("workspace_bytes", C.c_uint64),
+        ("loss", _vp), ("dloss", _vp), ("d_pred", _vp),
+    ]
+
+
 class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int32), ("total_ms", C.c_double)]
 
@@ -67,7 +76,8 @@ class KernelTime(C.Structure):
 EXPORTS = ["tdl_abi_version", "tdl_strerror", "tdl_launch_count", "tdl_profile_begin", "tdl_profile_end",
            "tdl_photo_ws_bytes", "tdl_photo_fwd", "tdl_photo_bwd",
            "tdl_feat_ws_bytes", "tdl_feat_fwd", "tdl_feat_bwd",
-           "tdl_edge_ws_bytes", "tdl_edge_smooth_fwd", "tdl_edge_smooth_bwd"]
+           "tdl_edge_ws_bytes", "tdl_edge_smooth_fwd", "tdl_edge_smooth_bwd",
+           "tdl_recon_ws_bytes", "tdl_recon_fwd", "tdl_recon_bwd"]
 
 _lib = None
 
@@ -97,11 +107,14 @@ def lib():
     L.tdl_photo_ws_bytes.argtypes = [C.c_int32] * 5 + [C.POINTER(C.c_int32)] * 2
     L.tdl_feat_ws_bytes.restype = C.c_uint64
     L.tdl_feat_ws_bytes.argtypes = [C.c_int32] * 5
+    L.tdl_recon_ws_bytes.restype = C.c_uint64
+    L.tdl_recon_ws_bytes.argtypes = []
     L.tdl_edge_ws_bytes.restype = C.c_uint64
     L.tdl_edge_ws_bytes.argtypes = [C.c_int32] * 4
     for name, T in (("tdl_photo_fwd", PhotoArgs), ("tdl_photo_bwd", PhotoArgs),
                     ("tdl_feat_fwd", FeatArgs), ("tdl_feat_bwd", FeatArgs),
-                    ("tdl_edge_smooth_fwd", EdgeArgs), ("tdl_edge_smooth_bwd", EdgeArgs)):
+                    ("tdl_edge_smooth_fwd", EdgeArgs), ("tdl_edge_smooth_bwd", EdgeArgs),
+                    ("tdl_recon_fwd", ReconArgs), ("tdl_recon_bwd", ReconArgs)):
         fn = getattr(L, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(T), C.c_void_p]

@@ -195,6 +195,8 @@ int tdl_launch_count(const char* entry) {
     if (!strcmp(entry, "tdl_feat_bwd")) return 1;
     if (!strcmp(entry, "tdl_edge_smooth_fwd")) return 3;  // area pyramid, smooth_fwd, finalize
     if (!strcmp(entry, "tdl_edge_smooth_bwd")) return 1;
+    if (!strcmp(entry, "tdl_recon_fwd")) return 2;        // recon_fwd, finalize
+    if (!strcmp(entry, "tdl_recon_bwd")) return 1;
     return 0;
 }
 
@@ -393,6 +395,39 @@ int tdl_edge_smooth_bwd(const tdl_edge_args* a, tdl_stream_t stream) {
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("edge_smooth_bwd", launch_smooth_bwd(sm, st));
+    return TDL_OK;
+}
+
+// ------------------------------------------------------------------------------------ masked reconstruction
+uint64_t tdl_recon_ws_bytes(void) { return 256; }
+
+static int check_recon(const tdl_recon_args* a, bool bwd, ReconArgsDev* d) {
+    if (!a) return TDL_ERR_NULL;
+    if (a->B < 1 || a->h < 4 || a->w < 4) return TDL_ERR_SHAPE;
+    if (!a->pred || !a->target || !a->workspace || !a->loss) return TDL_ERR_NULL;
+    if (a->workspace_bytes < tdl_recon_ws_bytes()) return TDL_ERR_WORKSPACE;
+    if (bwd && (!a->dloss || !a->d_pred)) return TDL_ERR_NULL;
+    *d = ReconArgsDev{a->B, a->h, a->w, a->coef, a->pred, a->target, a->mask,
+                      reinterpret_cast<double*>(a->workspace), a->loss, a->dloss, a->d_pred};
+    return TDL_OK;
+}
+
+int tdl_recon_fwd(const tdl_recon_args* a, tdl_stream_t stream) {
+    ReconArgsDev d;
+    const int rc = check_recon(a, false, &d);
+    if (rc != TDL_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDL_KERNEL("memset", cudaMemsetAsync(d.acc, 0, 2 * sizeof(double), st));
+    TDL_KERNEL("recon_fwd", launch_recon_fwd(d, st));
+    return TDL_OK;
+}
+
+int tdl_recon_bwd(const tdl_recon_args* a, tdl_stream_t stream) {
+    ReconArgsDev d;
+    const int rc = check_recon(a, true, &d);
+    if (rc != TDL_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDL_KERNEL("recon_bwd", launch_recon_bwd(d, st));
     return TDL_OK;
 }
 

@@ -89,6 +89,21 @@ struct FeatDev {
     float* dP;
 };
 
+// ---- masked image-reconstruction loss (TripleD family) ----------------------------------------------------
+struct ReconArgsDev {
+    int B, h, w;
+    float coef;
+    const float* pred;
+    const float* tgt;
+    const float* mask;
+    double* acc;
+    float* loss;
+    const float* dloss;
+    float* d_pred;
+};
+cudaError_t launch_recon_fwd(const ReconArgsDev& a, cudaStream_t st);
+cudaError_t launch_recon_bwd(const ReconArgsDev& a, cudaStream_t st);
+
 // launchers (each returns the cudaError_t of its launch)
 cudaError_t launch_photo_fwd(const PhotoDev& p, cudaStream_t st);
 bool photo_fwd_can_split(const PhotoDev& p);

@@ -580,6 +580,46 @@ __global__ void __launch_bounds__(kNT, 2) photo_score_kernel(const PhotoDev p, c
     }
 }
 
+
+// SSIM window adjoint: for the 3x3 window centred at xs / ys (pitch PITCH) returns k * (dS/dmu_x, dS/dE[x^2],
+// dS/dE[xy]) (G_mu, G_a, G_c), zero where torch.clamp blocks the gradient.  The window
+// statistics use the forward's row-major order so that the clamp decision is the forward's.
+template <int PITCH>
+TDL_DEV void window_adjoint(const float* __restrict__ xs, const float* __restrict__ ys, float k, float& cA, float& cB,
+                            float& cC) {
+    float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const float xv = xs[dy * PITCH + dx], yv = ys[dy * PITCH + dx];
+            const bool first = dy == -1 && dx == -1;
+            sx = first ? xv : __fadd_rn(sx, xv);
+            sy = first ? yv : __fadd_rn(sy, yv);
+            sxx = first ? __fmul_rn(xv, xv) : __fadd_rn(sxx, __fmul_rn(xv, xv));
+            syy = first ? __fmul_rn(yv, yv) : __fadd_rn(syy, __fmul_rn(yv, yv));
+            sxy = first ? __fmul_rn(xv, yv) : __fadd_rn(sxy, __fmul_rn(xv, yv));
+        }
+    }
+    const float mu_x = div9(sx), mu_y = div9(sy);
+    const float sg_x = __fsub_rn(div9(sxx), __fmul_rn(mu_x, mu_x));
+    const float sg_y = __fsub_rn(div9(syy), __fmul_rn(mu_y, mu_y));
+    const float sg_xy = __fsub_rn(div9(sxy), __fmul_rn(mu_x, mu_y));
+    const float n1 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, mu_x), mu_y), kSsimC1);
+    const float n2 = __fadd_rn(__fmul_rn(2.f, sg_xy), kSsimC2);
+    const float d1 = __fadd_rn(__fadd_rn(__fmul_rn(mu_x, mu_x), __fmul_rn(mu_y, mu_y)), kSsimC1);
+    const float d2 = __fadd_rn(__fadd_rn(sg_x, sg_y), kSsimC2);
+    const float n = __fmul_rn(n1, n2), d = __fmul_rn(d1, d2);
+    const float v = __fmul_rn(__fsub_rn(1.f, div_rn(n, d)), 0.5f);        // identical to the forward
+    cA = cB = cC = 0.f;
+    if (v >= 0.f && v <= 1.f) {                                            // clamp passes gradient inside [0,1]
+        const float rd = __frcp_rn(d);
+        cA = k * ((-mu_y * (n2 - n1) + (n * rd) * mu_x * (d2 - d1)) * rd);
+        cB = k * (n * d1 * 0.5f * rd * rd);
+        cC = k * (-n1 * rd);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Backward.
 // Backward tile: halo 2 in y, and in x a left margin of 4 so that the TMA box starts on a 16-byte boundary
@@ -768,45 +808,9 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
             const int q = s_list[e];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                float cA = 0.f, cB = 0.f, cC = 0.f;
-                {
-                    const float* xs = s_wrp + f * QGROUP + ch * QPLANE + q;
-                    const float* ys = s_tgt + ch * QPLANE + q;
-                    float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy) {          // row-major, like the forward (sum9)
-#pragma unroll
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            const float xv = xs[dy * QW + dx], yv = ys[dy * QW + dx];
-                            const bool first = dy == -1 && dx == -1;
-                            sx = first ? xv : __fadd_rn(sx, xv);
-                            sy = first ? yv : __fadd_rn(sy, yv);
-                            sxx = first ? __fmul_rn(xv, xv) : __fadd_rn(sxx, __fmul_rn(xv, xv));
-                            syy = first ? __fmul_rn(yv, yv) : __fadd_rn(syy, __fmul_rn(yv, yv));
-                            sxy = first ? __fmul_rn(xv, yv) : __fadd_rn(sxy, __fmul_rn(xv, yv));
-                        }
-                    }
-                    const float mu_x = div9(sx), mu_y = div9(sy);
-                    const float sg_x = __fsub_rn(div9(sxx), __fmul_rn(mu_x, mu_x));
-                    const float sg_y = __fsub_rn(div9(syy), __fmul_rn(mu_y, mu_y));
-                    const float sg_xy = __fsub_rn(div9(sxy), __fmul_rn(mu_x, mu_y));
-                    const float n1 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, mu_x), mu_y), kSsimC1);
-                    const float n2 = __fadd_rn(__fmul_rn(2.f, sg_xy), kSsimC2);
-                    const float d1 = __fadd_rn(__fadd_rn(__fmul_rn(mu_x, mu_x), __fmul_rn(mu_y, mu_y)), kSsimC1);
-                    const float d2 = __fadd_rn(__fadd_rn(sg_x, sg_y), kSsimC2);
-                    const float n = __fmul_rn(n1, n2), d = __fmul_rn(d1, d2);
-                    const float v = __fmul_rn(__fsub_rn(1.f, div_rn(n, d)), 0.5f);     // identical to the forward
-                    if (v >= 0.f && v <= 1.f) {                           // clamp passes gradient inside [0,1]
-                        const float rd = __frcp_rn(d);
-                        const float gmu = (-mu_y * (n2 - n1) + (n * rd) * mu_x * (d2 - d1)) * rd;
-                        const float ga = n * d1 * 0.5f * rd * rd;
-                        const float gc = -n1 * rd;
-                        const float k = g_ssim * (1.f / 9.f);
-                        cA = k * gmu;
-                        cB = k * ga;
-                        cC = k * gc;
-                    }
-                }
+                float cA, cB, cC;
+                window_adjoint<QW>(s_wrp + f * QGROUP + ch * QPLANE + q, s_tgt + ch * QPLANE + q,
+                                   g_ssim * (1.f / 9.f), cA, cB, cC);
                 s_coef[(ch * 3 + 0) * QPLANE + q] = cA;
                 s_coef[(ch * 3 + 1) * QPLANE + q] = cB;
                 s_coef[(ch * 3 + 2) * QPLANE + q] = cC;
@@ -1089,6 +1093,204 @@ cudaError_t launch_photo_bwd(const PhotoDev& p, cudaStream_t st) {
         case 4: return launch_bwd_t<4>(p, st);
     }
     return cudaErrorInvalidValue;
+}
+
+
+// ================================================================================================
+// Masked image-reconstruction loss of the TripleD family (mono/model/mono_fm_joint_inpaint/net.py:80-91):
+//     rho = 0.85 * mean_c SSIM(pred, tgt) + 0.15 * mean_c robust_l1(pred, tgt)            (B,1,h,w)
+//     loss = coef * sum(rho * (1 - mask)) / sum(1 - mask)            mask (B,3,h,w) broadcasts over rho
+// Forward: 32x32 tiles, reflect halo 1, the strip SSIM of the photometric path.  Backward: halo 2, window adjoint
+// coefficients for every window, box-sum gather, dense store of d_pred (no atomics).
+// ================================================================================================
+struct ReconDev {
+    int B, h, w;
+    float coef;
+    const float* pred;
+    const float* tgt;
+    const float* mask;       // may be null: plain mean over (B,1,h,w)
+    double* acc;             // [2]: numerator, denominator
+    float* loss;
+    const float* dloss;
+    float* d_pred;
+};
+
+TDL_DEV float recon_weight(const ReconDev& p, int b, size_t hw, size_t pix) {
+    if (!p.mask) return 1.f;
+    const float* m = p.mask + (size_t)b * 3 * hw + pix;
+    return (1.f - __ldg(m)) + (1.f - __ldg(m + hw)) + (1.f - __ldg(m + 2 * hw));
+}
+
+__global__ void __launch_bounds__(kNT, 2) recon_fwd_kernel(const ReconDev p) {
+    constexpr int PW = kTW + 2, PH = kTH + 2, PLANE = PW * PH;
+    extern __shared__ float smem_recon[];
+    float* s_tgt = smem_recon;                    // [3][PLANE]
+    float* s_prd = smem_recon + 3 * PLANE;        // [3][PLANE]
+    float* s_stats = smem_recon + 6 * PLANE + threadIdx.x;
+    __shared__ float s_red[32];
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int b = blockIdx.z, tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
+    const int H = p.h, W = p.w;
+    const size_t HW = (size_t)H * W;
+    for (int i = tid; i < PLANE; i += kNT) {
+        const int r = i / PW, c = i - r * PW;
+        const size_t o = (size_t)b * 3 * HW + (size_t)reflect1(ty0 - 1 + r, H) * W + reflect1(tx0 - 1 + c, W);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            s_tgt[ch * PLANE + i] = __ldg(p.tgt + o + ch * HW);
+            s_prd[ch * PLANE + i] = __ldg(p.pred + o + ch * HW);
+        }
+    }
+    __syncthreads();
+    const int r0 = wrp * kR, gx = tx0 + lane;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float mu_y[kR], sg_y[kR];
+        strip_target_stats<PW>(s_tgt + ch * PLANE, r0, lane, mu_y, sg_y);
+#pragma unroll
+        for (int i = 0; i < kR; ++i) {
+            s_stats[((ch * 2) * kR + i) * kNT] = mu_y[i];
+            s_stats[((ch * 2 + 1) * kR + i) * kNT] = sg_y[i];
+        }
+    }
+    float rho[kR];
+    strip_reprojection<PW>(s_prd, s_tgt, PLANE, r0, lane, s_stats, rho);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+        const int gy = ty0 + r0 + i;
+        if (gx < W && gy < H) {
+            const float wq = recon_weight(p, b, HW, (size_t)gy * W + gx);
+            num += rho[i] * wq;
+            den += wq;
+        }
+    }
+    num = block_sum(num, s_red);
+    if (tid == 0) atomicAdd(p.acc, (double)num);
+    den = block_sum(den, s_red);
+    if (tid == 0) atomicAdd(p.acc + 1, (double)den);
+}
+
+__global__ void recon_finalize_kernel(const double* acc, float coef, float* loss) {
+    if (threadIdx.x == 0) loss[0] = __fmul_rn(coef, (float)(acc[0] / acc[1]));
+}
+
+__global__ void __launch_bounds__(kNT, 2) recon_bwd_kernel(const ReconDev p) {
+    constexpr int QW = kTW + 4, QH = kTH + 4, QPLANE = QW * QH;
+    constexpr int PW = kTW + 2, PH = kTH + 2;
+    extern __shared__ float smem_recon[];
+    float* s_tgt = smem_recon;                    // [3][QPLANE]
+    float* s_prd = s_tgt + 3 * QPLANE;            // [3][QPLANE]
+    float* s_coef = s_prd + 3 * QPLANE;           // [3 ch][3 coef][QPLANE]
+    float* s_wq = s_coef + 9 * QPLANE;            // [QPLANE] window weight sum_c (1 - mask), 0 outside the image
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int b = blockIdx.z, tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
+    const int H = p.h, W = p.w;
+    const size_t HW = (size_t)H * W;
+    const float up = __ldg(p.dloss) * p.coef / (float)p.acc[1];
+    for (int i = tid; i < QPLANE; i += kNT) {
+        const int r = i / QW, c = i - r * QW;
+        const int ry = ty0 - 2 + r, rx = tx0 - 2 + c;
+        const bool inside = ry >= 0 && ry < H && rx >= 0 && rx < W;
+        const size_t pix = (size_t)reflect1(ry, H) * W + reflect1(rx, W);
+        const size_t o = (size_t)b * 3 * HW + pix;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            s_tgt[ch * QPLANE + i] = __ldg(p.tgt + o + ch * HW);
+            s_prd[ch * QPLANE + i] = __ldg(p.pred + o + ch * HW);
+        }
+        s_wq[i] = inside ? recon_weight(p, b, HW, pix) : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < PH * PW; i += kNT) {
+        const int r = i / PW, c = i - r * PW;
+        const int q = (r + 1) * QW + (c + 1);
+        const float k = up * s_wq[q] * (0.85f / 3.f) * (1.f / 9.f);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float cA = 0.f, cB = 0.f, cC = 0.f;
+            if (k != 0.f) window_adjoint<QW>(s_prd + ch * QPLANE + q, s_tgt + ch * QPLANE + q, k, cA, cB, cC);
+            s_coef[(ch * 3 + 0) * QPLANE + q] = cA;
+            s_coef[(ch * 3 + 1) * QPLANE + q] = cB;
+            s_coef[(ch * 3 + 2) * QPLANE + q] = cC;
+        }
+    }
+    __syncthreads();
+    const int r0 = wrp * kR, gx = tx0 + lane, qc = lane + 2;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float box[3][kR];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float* pl = s_coef + (ch * 3 + k) * QPLANE + (r0 + 1) * QW + qc;
+            float hsum[kR + 2];
+#pragma unroll
+            for (int j = 0; j < kR + 2; ++j) hsum[j] = pl[j * QW - 1] + pl[j * QW] + pl[j * QW + 1];
+#pragma unroll
+            for (int i = 0; i < kR; ++i) box[k][i] = hsum[i] + hsum[i + 1] + hsum[i + 2];
+        }
+#pragma unroll
+        for (int i = 0; i < kR; ++i) {
+            const int gy = ty0 + r0 + i;
+            if (gx >= W || gy >= H) continue;
+            const int q = (r0 + i + 2) * QW + qc;
+            const bool bx0 = gx == 1, bx1 = gx == W - 2, by0 = gy == 1, by1 = gy == H - 2;
+            if (bx0 || bx1 || by0 || by1) {                       // reflect-padding multiplicity (see photo_bwd_kernel)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float* c = s_coef + (ch * 3 + k) * QPLANE + q;
+                    float e = 0.f;
+                    if (bx0) e += c[-QW - 1] + c[-1] + c[QW - 1];
+                    if (bx1) e += c[-QW + 1] + c[1] + c[QW + 1];
+                    if (by0) e += c[-QW - 1] + c[-QW] + c[-QW + 1];
+                    if (by1) e += c[QW - 1] + c[QW] + c[QW + 1];
+                    if (bx0 && by0) e += c[-QW - 1];
+                    if (bx1 && by0) e += c[-QW + 1];
+                    if (bx0 && by1) e += c[QW - 1];
+                    if (bx1 && by1) e += c[QW + 1];
+                    box[k][i] += e;
+                }
+            }
+            const float xv = s_prd[ch * QPLANE + q], yv = s_tgt[ch * QPLANE + q];
+            const float df = xv - yv;
+            const float g = box[0][i] + 2.f * xv * box[1][i] + yv * box[2][i] +
+                            up * s_wq[q] * (0.15f / 3.f) * df * rsqrtf(df * df + kL1Eps2);
+            p.d_pred[((size_t)b * 3 + ch) * HW + (size_t)gy * W + gx] = g;
+        }
+    }
+}
+
+cudaError_t launch_recon_fwd(const ReconArgsDev& a, cudaStream_t st) {
+    ReconDev p{a.B, a.h, a.w, a.coef, a.pred, a.tgt, a.mask, a.acc, a.loss, a.dloss, a.d_pred};
+    constexpr int PLANE = (kTW + 2) * (kTH + 2);
+    const size_t smem = (size_t)6 * PLANE * sizeof(float) + (size_t)6 * kR * kNT * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(recon_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((a.w + kTW - 1) / kTW, (a.h + kTH - 1) / kTH, a.B);
+    recon_fwd_kernel<<<grid, kNT, smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    recon_finalize_kernel<<<1, 32, 0, st>>>(a.acc, a.coef, a.loss);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_recon_bwd(const ReconArgsDev& a, cudaStream_t st) {
+    ReconDev p{a.B, a.h, a.w, a.coef, a.pred, a.tgt, a.mask, a.acc, a.loss, a.dloss, a.d_pred};
+    constexpr int QPLANE = (kTW + 4) * (kTH + 4);
+    const size_t smem = (size_t)16 * QPLANE * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(recon_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((a.w + kTW - 1) / kTW, (a.h + kTH - 1) / kTH, a.B);
+    recon_bwd_kernel<<<grid, kNT, smem, st>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace tdl

@@ -29,8 +29,10 @@ from typing import Dict, Optional, Sequence
 import torch
 
 from .geometry import half_res_intrinsics, projection_matrix
-from .ops import (EdgeAwareSmoothness, EdgeConfig, FeatConfig, FeatureMetricLoss, PhotoConfig,
-                  PhotometricSmoothLoss)
+import torch.nn.functional as F
+
+from .ops import (EdgeAwareSmoothness, EdgeConfig, FeatConfig, FeatureMetricLoss, MaskedReconstructionLoss,
+                  PhotoConfig, PhotometricSmoothLoss)
 
 
 class LossDict(dict):
@@ -217,9 +219,31 @@ class ViewSynthesisLossMixin:
             loss_dict.add_part(per)
             if idx is not None:
                 outputs["min_index"] = idx
+        w_rec = _opt_get(opt, "img_reconstruct_weight", 1)
+        if features is not None and w_rec != 0:
+            mask = inputs[("mask", 0, 0)]
+            for s in opt.scales:                 # autoencoder / in-painting term (net.py:80-91)
+                res = outputs[("res_img", 0, s)]
+                size = list(res.shape[-2:])
+                tgt_r = F.interpolate(target, size, mode="bilinear", align_corners=False)
+                msk_r = F.interpolate(mask, size, mode="bilinear", align_corners=False)
+                rec = MaskedReconstructionLoss.apply(float(w_rec) / len(opt.scales), res, tgt_r, msk_r)[0]
+                loss_dict[("img_reconstruct_loss", s)] = rec
+                loss_dict.add_part(rec)
         base = self.compute_losses_baseline(inputs, outputs, noise)
         loss_dict.update(base)
         loss_dict._parts += base._parts
+        return loss_dict
+
+    def compute_auto_res_loss(self, inputs, outputs):
+        """mono/model/mono_fm_joint_inpaint/net.py:520-527: one element-wise robust L1 (left to PyTorch);
+        like the reference the entry is the un-reduced (B,1,H,W) map, which batch_processor averages."""
+        loss_dict = {}
+        if _opt_get(self.opt, "auto_res_weight", 0.0) > 0.0:
+            target = inputs[("color", 0, 0)]
+            res = outputs[("auto_res_img", 0, 0)]
+            l1 = torch.sqrt(torch.pow(res - target, 2) + 1e-3 ** 2).mean(1, True)
+            loss_dict["auto_res_loss"] = l1 * self.opt.auto_res_weight
         return loss_dict
 
     def get_feature_regularization_loss(self, feature, img):

@@ -13,7 +13,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import EdgeArgs, FeatArgs, PhotoArgs, TDL_MAX_SCALES, TDL_MAX_SRC
+from ._lib import EdgeArgs, FeatArgs, PhotoArgs, ReconArgs, TDL_MAX_SCALES, TDL_MAX_SRC
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -317,3 +317,54 @@ class EdgeAwareSmoothness(torch.autograd.Function):
         with torch.cuda.device(feature.device):
             _lib.check(L.tdl_edge_smooth_bwd(C.byref(a), _stream()), "tdl_edge_smooth_bwd")
         return None, d_feat, None
+
+
+# --------------------------------------------------------------------------------------------------
+class MaskedReconstructionLoss(torch.autograd.Function):
+    """img_reconstruct_loss of the TripleD family (mono/model/mono_fm_joint_inpaint/net.py:80-91):
+    forward(coef, pred (B,3,h,w), target (B,3,h,w), mask (B,3,h,w) | None) -> loss[1] =
+    coef * sum(rho(pred, target) * (1 - mask)) / sum(1 - mask); gradient w.r.t. pred only."""
+
+    @staticmethod
+    def forward(ctx, coef: float, pred, target, mask):
+        L = _lib.lib()
+        pred = _f32c(pred, "pred")
+        target = _f32c(target, "target")
+        mask = None if mask is None else _f32c(mask, "mask")
+        if target.shape != pred.shape or pred.shape[1] != 3 or (mask is not None and mask.shape != pred.shape):
+            raise _lib.TdlError("pred / target / mask must all be (B,3,h,w)")
+        a, ws = MaskedReconstructionLoss._args(L, coef, pred, target, mask)
+        loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+        a.loss = loss.data_ptr()
+        with torch.cuda.device(pred.device):
+            _lib.check(L.tdl_recon_fwd(C.byref(a), _stream()), "tdl_recon_fwd")
+        ctx.coef = coef
+        ctx.has_mask = mask is not None
+        ctx.save_for_backward(pred, target, ws, *([mask] if mask is not None else []))
+        return loss
+
+    @staticmethod
+    def _args(L, coef, pred, target, mask, ws=None):
+        a = ReconArgs()
+        a.B, a.h, a.w, a.coef = pred.shape[0], pred.shape[2], pred.shape[3], coef
+        a.pred, a.target = pred.data_ptr(), target.data_ptr()
+        if mask is not None:
+            a.mask = mask.data_ptr()
+        if ws is None:
+            ws = torch.empty(L.tdl_recon_ws_bytes(), dtype=torch.uint8, device=pred.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        return a, ws
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        L = _lib.lib()
+        pred, target, ws = ctx.saved_tensors[:3]
+        mask = ctx.saved_tensors[3] if ctx.has_mask else None
+        a, _ = MaskedReconstructionLoss._args(L, ctx.coef, pred, target, mask, ws)
+        scratch = torch.empty(1, dtype=torch.float32, device=pred.device)
+        g_loss = _f32c(g_loss, "grad")
+        d_pred = torch.empty_like(pred)
+        a.loss, a.dloss, a.d_pred = scratch.data_ptr(), g_loss.data_ptr(), d_pred.data_ptr()
+        with torch.cuda.device(pred.device):
+            _lib.check(L.tdl_recon_bwd(C.byref(a), _stream()), "tdl_recon_bwd")
+        return None, d_pred, None, None
