@@ -46,8 +46,13 @@ TDL_DEV float div_rn(float n, float d) {
 }
 // sqrt(x) for x in [1e-7, 1e2]: rsqrt seed + one Newton step on the residual (correctly rounded except for
 // rare last-bit ties); __fsqrt_rn's IEEE sequence was 5 % of the forward's instructions (line profile, r1)
+TDL_DEV float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // MUFU.RSQ alone (rsqrtf() adds denormal handling)
+    return r;
+}
 TDL_DEV float sqrt_fast(float x) {
-    const float r = rsqrtf(x);
+    const float r = rsqrt_approx(x);
     const float s = x * r;
     return fmaf(fmaf(-s, s, x), 0.5f * r, s);
 }

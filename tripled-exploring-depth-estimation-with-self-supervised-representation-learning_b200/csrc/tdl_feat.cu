@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
                 const float dix = -v00 * bt.ey + v01 * bt.ey - v10 * bt.ay + v11 * bt.ay;
                 const float diy = -v00 * bt.ex - v01 * bt.ax + v10 * bt.ex + v11 * bt.ax;
                 const float df = val - t[j];
-                const float gvv = up * df * rsqrtf(df * df + kL1Eps2);      // d loss / d warped value
+                const float gvv = up * df * rsqrt_approx(df * df + kL1Eps2);      // d loss / d warped value
                 gix += gvv * dix;
                 giy += gvv * diy;
                 if (kGradFeat) {

@@ -863,7 +863,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
                     float g = box[0][i] + 2.f * xv * box[1][i] + yv * box[2][i];
                     if (s_mask[q] == chan) {
                         const float df = xv - yv;
-                        g += g_l1 * df * rsqrtf(df * df + kL1Eps2);
+                        g += g_l1 * df * rsqrt_approx(df * df + kL1Eps2);
                     }
                     G[ch][i] = g;
                 }
@@ -1254,7 +1254,7 @@ __global__ void __launch_bounds__(kNT, 2) recon_bwd_kernel(const ReconDev p) {
             const float xv = s_prd[ch * QPLANE + q], yv = s_tgt[ch * QPLANE + q];
             const float df = xv - yv;
             const float g = box[0][i] + 2.f * xv * box[1][i] + yv * box[2][i] +
-                            up * s_wq[q] * (0.15f / 3.f) * df * rsqrtf(df * df + kL1Eps2);
+                            up * s_wq[q] * (0.15f / 3.f) * df * rsqrt_approx(df * df + kL1Eps2);
             p.d_pred[((size_t)b * 3 + ch) * HW + (size_t)gy * W + gx] = g;
         }
     }
