@@ -72,6 +72,15 @@ class ViewSynthesisLossMixin:
     grid_sample_align_corners = False   # torch >= 1.3 default, which is what the reference runs with today
     _smooth_weight_key = "smoothness_weight"
     _noise_calls = 0
+    overlap_streams = True              # feature-metric kernels on a second stream (see compute_losses_fm)
+    _streams = {}
+
+    def _side_stream(self, device):
+        key = (device.type, device.index)
+        st = ViewSynthesisLossMixin._streams.get(key)
+        if st is None:
+            st = ViewSynthesisLossMixin._streams[key] = torch.cuda.Stream(device)
+        return st
 
     # ------------------------------------------------------------------ helpers
     def _src_frames(self):
@@ -183,12 +192,24 @@ class ViewSynthesisLossMixin:
         evaluated once and the same loss tensor is returned under every ('min_perceptional_loss', s)."""
         opt = self.opt
         scales = list(opt.scales)
-        loss_dict = self.compute_losses_baseline(inputs, outputs, noise)
         if src_fs is None:
             src_fs = {f: self._extract(inputs[("color", f, 0)]) for f in self._src_frames()}
         if tgt_f is None:
             tgt_f = self._extract(inputs[("color", 0, 0)])
-        per, idx = self._feature_metric(inputs, outputs, tgt_f, src_fs, opt.perception_weight / len(scales))
+        # The feature-metric kernels (HBM / L2-atomic bound) and the photometric kernels (instruction bound) are
+        # independent until the losses are summed: issue them on two streams so that they share the SMs.  Autograd
+        # runs each backward on its forward's stream, so the backward kernels overlap the same way.
+        side = self._side_stream(tgt_f.device) if self.overlap_streams else None
+        if side is not None:
+            main = torch.cuda.current_stream(tgt_f.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                per, idx = self._feature_metric(inputs, outputs, tgt_f, src_fs, opt.perception_weight / len(scales))
+            loss_dict = self.compute_losses_baseline(inputs, outputs, noise)
+            main.wait_stream(side)
+        else:
+            loss_dict = self.compute_losses_baseline(inputs, outputs, noise)
+            per, idx = self._feature_metric(inputs, outputs, tgt_f, src_fs, opt.perception_weight / len(scales))
         ordered = LossDict()
         ordered._parts = list(loss_dict._parts)
         ordered.add_part(per, len(scales))
