@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-train", action="store_true", help="skip the full train-step measurement")
     ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--eager-train", action="store_true", help="do not CUDA-graph the train step")
+    ap.add_argument("--train-model", default="mono_fm", choices=["mono_fm", "tripled"],
+                    help="mono_fm = cfg_kitti_fm (BASELINE configs[1]); tripled = cfg_kitti_tripleD (configs[2])")
     ap.add_argument("--syncbn", action="store_true",
                     help="convert to SyncBatchNorm like cfg_kitti_fm (syncbn = True); off by default: its ~200 tiny "
                          "collectives per step halve 2-GPU throughput (measured: 186 vs 394 images/s)")
@@ -295,11 +297,13 @@ def train_step_bench(args, device, rank, world, dist_on):
     importlib.import_module(PKG + ".nets")
     B, H, W = args.batch, args.height, args.width
     opt = opt_dict(B, H, W)
-    opt.update(name="mono_fm", depth_num_layers=50, pose_num_layers=18, extractor_num_layers=50,
-               extractor_pretrained_path=None)
+    tripled = args.train_model == "tripled"
+    name = "mono_fm_joint_inpaint_disentangle" if tripled else "mono_fm"
+    opt.update(name=name, depth_num_layers=50, pose_num_layers=18, extractor_num_layers=50,
+               extractor_pretrained_path=None, dis=1e-3, cvt=1e-3, auto_res_weight=5e-3, freeze_extractor=False)
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
-    model = tdl.MONO.module_dict["mono_fm"](tdl.config.ConfigDict(opt)).to(device).train()
+    model = tdl.MONO.module_dict[name](tdl.config.ConfigDict(opt)).to(device).train()
     n_params = sum(q.numel() for q in model.parameters() if q.requires_grad)
     syncbn = dist_on and args.syncbn
     if dist_on:
@@ -315,6 +319,13 @@ def train_step_bench(args, device, rank, world, dist_on):
             inputs[k[1]] = v.to(device)
     for f in FRAME_IDS:
         inputs[("color_aug", f, 0)] = inputs[("color", f, 0)]
+    if tripled:                                     # 16 erased 16x16 holes (cfg_kitti_tripleD.py:19-20)
+        g = torch.Generator().manual_seed(rank_seed(rank))
+        mask = torch.ones(B, 3, H, W)
+        for _ in range(16):
+            y0, x0 = int(torch.randint(0, H - 16, (1,), generator=g)), int(torch.randint(0, W - 16, (1,), generator=g))
+            mask[:, :, y0:y0 + 16, x0:x0 + 16] = 0
+        inputs[("mask", 0, 0)] = mask.to(device)
 
     def step():
         optim.zero_grad(set_to_none=True)
@@ -353,8 +364,10 @@ def train_step_bench(args, device, rank, world, dist_on):
     loss = run()
     return {"images_per_s": round(whole_job_images_per_s(world, B, args.train_steps, ms), 1),
             "ms_per_step": round(ms / args.train_steps, 3), "steps": args.train_steps, "execution": mode,
-            "model": "mono_fm (cfg_kitti_fm): ResNet-50 depth + ResNet-18 pose + ResNet-50 extractor (level 0), "
-                     f"{n_params / 1e6:.1f} M trainable params, eager PyTorch fp32 networks + fused loss, Adam",
+            "model": ("TripleD mono_fm_joint_inpaint_disentangle (cfg_kitti_tripleD): ResNet-50 depth + ResNet-18 pose + "
+                      "ResNet-50 in-loop encoder + image / colour decoders, " if tripled else
+                      "mono_fm (cfg_kitti_fm): ResNet-50 depth + ResNet-18 pose + ResNet-50 extractor (level 0), ")
+                     + f"{n_params / 1e6:.1f} M trainable params, PyTorch fp32 networks + fused loss, Adam",
             "parallelism": f"DDP x{world} (NCCL all-reduce of gradients" + (", SyncBatchNorm)" if syncbn else ")"),
             "final_loss": float(loss.detach())}
 

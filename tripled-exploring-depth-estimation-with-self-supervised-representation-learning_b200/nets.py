@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 from .geometry import transformation_from_parameters
 from .losses import ViewSynthesisLossMixin
-from .networks import DepthDecoder, PoseDecoder, ResnetEncoder
+from .networks import DepthDecoder, ImageDecoder, PoseDecoder, ResnetEncoder
 from .registry import MONO
 
 
@@ -73,3 +73,55 @@ class mono_fm(_DepthPoseNet):
 
     def compute_losses(self, inputs, outputs):
         return self.compute_losses_fm(inputs, outputs)
+
+
+@MONO.register_module
+class mono_fm_joint_inpaint(_DepthPoseNet):
+    """Joint depth + in-painting autoencoder net (mono/model/mono_fm_joint_inpaint/net.py:19-133): the feature
+    encoder is trained in the loop on the erased target, its decoder reconstructs the image at four scales."""
+
+    def __init__(self, options):
+        super().__init__(options)
+        self.Encoder = ResnetEncoder(self.opt.get("extractor_num_layers", 50))
+        self.Decoder = ImageDecoder(self.Encoder.num_ch_enc, "res_img")
+        if self.opt.get("freeze_extractor", False):
+            for q in self.Encoder.parameters():
+                q.requires_grad = False
+
+    def forward(self, inputs):
+        outputs = self.DepthDecoder(self.DepthEncoder(inputs["color_aug", 0, 0]))
+        if not self.training:
+            return outputs
+        outputs.update(self.predict_poses(inputs))
+        features = self.Encoder(inputs[("color", 0, 0)] * inputs[("mask", 0, 0)])       # net.py:40
+        if self.opt.get("img_reconstruct_weight", 1) != 0:
+            outputs.update(self.Decoder(features, 0))
+        self._decode_extra(inputs, outputs, features)
+        return outputs, self.compute_losses(inputs, outputs, features)
+
+    def _decode_extra(self, inputs, outputs, features):
+        pass
+
+    def compute_losses(self, inputs, outputs, features):
+        return self.compute_losses_joint_core(inputs, outputs, features)
+
+
+@MONO.register_module
+class mono_fm_joint_inpaint_disentangle(mono_fm_joint_inpaint):
+    """The TripleD net of config/cfg_kitti_tripleD.py (mono/model/mono_fm_joint_inpaint/net.py:398-532): adds a
+    colour decoder whose full-resolution output feeds auto_res_loss."""
+
+    def __init__(self, options):
+        super().__init__(options)
+        self.ColorDecoder = ImageDecoder(self.DepthEncoder.num_ch_enc, "auto_res_img")
+
+    def _decode_extra(self, inputs, outputs, features):
+        if self.opt.get("auto_res_weight", 0.0) > 0.0:
+            outputs.update(self.ColorDecoder(self.DepthEncoder(inputs["color_aug", 0, 0]), 0))
+
+    def compute_losses(self, inputs, outputs, features):
+        loss_dict = super().compute_losses(inputs, outputs, features)
+        for k, v in self.compute_auto_res_loss(inputs, outputs).items():
+            loss_dict[k] = v
+            loss_dict.add_part(v.mean())
+        return loss_dict

@@ -8,6 +8,8 @@ and timed; they follow the reference's interfaces (what goes in, which keys / sh
         (mono/model/mono_fm/depth_decoder.py:45-98)
   PoseDecoder(num_ch_enc)                       axisangle, translation (B, 2, 1, 3), scaled by 0.01
         (mono/model/mono_fm/pose_decoder.py:16-26)
+  ImageDecoder(num_ch_enc, key)                 {(key, 0, s): sigmoid RGB at H/2^s}, s = 0..3, from the deepest
+        encoder level (mono/model/mono_fm_joint/decoder.py:7-57 "res_img", :60-112 "auto_res_img")
 """
 from __future__ import annotations
 
@@ -101,3 +103,26 @@ class PoseDecoder(nn.Module):
     def forward(self, feats):
         pose = 0.01 * self.body(feats[-1]).mean((2, 3)).view(-1, self.num_frames, 1, 6)
         return pose[..., :3], pose[..., 3:]
+
+
+class ImageDecoder(nn.Module):
+    """Autoencoder / colour decoder of the joint nets: five (conv3x3 + ELU, x2 nearest up-sampling) stages from the
+    deepest encoder map back to full resolution, RGB heads on the last four."""
+
+    def __init__(self, num_ch_enc, key="res_img", widths=(256, 128, 64, 32, 16)):
+        super().__init__()
+        self.key = key
+        chans = [num_ch_enc[-1], *widths]
+        self.up = nn.ModuleList([nn.Sequential(nn.Conv2d(chans[i], chans[i + 1], 3, padding=1), nn.ELU(True),
+                                               nn.Upsample(scale_factor=2, mode="nearest"),
+                                               nn.Conv2d(chans[i + 1], chans[i + 1], 3, padding=1), nn.ELU(True))
+                                 for i in range(5)])
+        self.heads = nn.ModuleList([nn.Conv2d(w, 3, 3, padding=1) for w in widths[1:]])
+
+    def forward(self, feats, frame_id=0):
+        out, x = {}, feats[-1]
+        for i, stage in enumerate(self.up):
+            x = stage(x)
+            if i >= 1:                                   # stages 1..4 are at H/8, H/4, H/2, H
+                out[(self.key, frame_id, 4 - i)] = torch.sigmoid(self.heads[i - 1](x))
+        return out
