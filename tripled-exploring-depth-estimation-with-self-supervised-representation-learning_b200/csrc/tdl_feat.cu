@@ -134,8 +134,13 @@ template <bool kGradFeat>
 __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
     __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
     __shared__ float s_dP[TDL_MAX_SRC * 12];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int b = blockIdx.y;
+    // CTA = 32 columns x 4 consecutive rows (one warp per row): the south taps of row r are the north taps of
+    // row r + 1 wherever the flow is regular, so they are handed down through shared memory and only the last
+    // row of the CTA sends its south taps to L2 (5 instead of 8 reductions per element column and channel).
+    __shared__ int s_o00[kFeatNT], s_fs[kFeatNT];
+    __shared__ float s_bot[4][kFeatNT];
+    const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5;
+    const int b = blockIdx.z;
     const int h = p.h, w = p.w, C = p.C, S = p.S;
     const size_t hw = (size_t)h * w;
     if (tid < S * 12) {
@@ -144,9 +149,10 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
     }
     if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
     __syncthreads();
-    const int pix = blockIdx.x * kFeatNT + tid;
-    const bool active = pix < (int)hw;
-    const int y = active ? pix / w : 0, x = active ? pix - y * w : 0;
+    const int xq = blockIdx.x * 32 + lane, yq = blockIdx.y * 4 + wr;
+    const bool active = xq < w && yq < h;
+    const int y = active ? yq : 0, x = active ? xq : 0;
+    const int pix = y * w + x;
     const int fsel = active ? p.argmin[(size_t)b * hw + pix] : -1;
     const DepthParams dp{p.min_disp, p.range};
     const UpTap ut = up_tap(y, x, p.sy, p.sx, p.dh, p.dw);
@@ -175,9 +181,20 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
         absorbs = __shfl_up_sync(0xffffffffu, (int)absorbed, 1) != 0 && lane > 0;
     }
 
-    constexpr int CB = 8;
+    // vertical pattern: the row below samples one source row further down in the same source column
+    bool gives_down = false, takes_up = false;
+    if (kGradFeat && dsb) {
+        s_o00[tid] = active ? o00 : -1;
+        s_fs[tid] = fsel;
+        __syncthreads();
+        if (wr < 3) gives_down = active && bt.vy && s_fs[tid + 32] == fsel && s_o00[tid + 32] == o00 + w;
+        if (wr > 0) takes_up = active && s_fs[tid - 32] == fsel && s_fs[tid - 32] >= 0 && s_o00[tid - 32] + w == o00 &&
+                               s_o00[tid - 32] >= 0;
+    }
+
+    constexpr int CB = 4;
     // block-uniform 64-bit bases + 32-bit per-thread offsets (one integer add per access)
-    const unsigned uhw = (unsigned)hw, upix = (unsigned)min(pix, (int)hw - 1);
+    const unsigned uhw = (unsigned)hw, upix = (unsigned)pix;
     const float* tbase = p.tgt + (size_t)b * C * hw;
     const float* sbb = sb + (size_t)b * C * hw;
     float* dtb = (kGradFeat && p.d_tgt) ? p.d_tgt + (size_t)b * C * hw : nullptr;
@@ -194,8 +211,10 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
             v[j][2] = active ? __ldg(sbb + (co + (unsigned)o10)) : 0.f;
             v[j][3] = active ? __ldg(sbb + (co + (unsigned)o11)) : 0.f;
         }
+        float topv[CB], botv[CB], etop[CB], ebot[CB];
 #pragma unroll
         for (int j = 0; j < CB; ++j) {
+            topv[j] = botv[j] = etop[j] = ebot[j] = 0.f;
             if (c0 + j < C) {                                             // uniform across the warp
                 const unsigned co = (unsigned)(c0 + j) * uhw;
                 // zero weight <=> clamped tap: same arithmetic as bilin_sample_grad with the tap skipped
@@ -212,20 +231,36 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
                     if (dtb && active) dtb[co + upix] = -gvv;
                     if (dsbb) {
                         float top = gvv * bt.nw, bot = gvv * bt.sw;
-                        const float e_top = gvv * bt.ne, e_bot = gvv * bt.se;
-                        const float in_top = __shfl_up_sync(0xffffffffu, e_top, 1);
-                        const float in_bot = __shfl_up_sync(0xffffffffu, e_bot, 1);
+                        etop[j] = gvv * bt.ne;
+                        ebot[j] = gvv * bt.se;
+                        const float in_top = __shfl_up_sync(0xffffffffu, etop[j], 1);
+                        const float in_bot = __shfl_up_sync(0xffffffffu, ebot[j], 1);
                         if (absorbs) {
                             top += in_top;
                             bot += in_bot;
                         }
-                        if (active) {
-                            atomicAdd(dsbb + (co + (unsigned)o00), top);
-                            if (bt.vy) atomicAdd(dsbb + (co + (unsigned)o10), bot);
-                            if (!absorbed && bt.vx) {
-                                atomicAdd(dsbb + (co + (unsigned)o01), e_top);
-                                if (bt.vy) atomicAdd(dsbb + (co + (unsigned)o11), e_bot);
-                            }
+                        topv[j] = top;
+                        botv[j] = bot;
+                    }
+                }
+            }
+        }
+        if (kGradFeat && dsbb) {                  // dsbb is non-null for every lane or for none
+            __syncthreads();                       // the previous batch's s_bot has been consumed
+#pragma unroll
+            for (int j = 0; j < CB; ++j) s_bot[j][tid] = gives_down ? botv[j] : 0.f;
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < CB; ++j) {
+                    if (c0 + j < C) {
+                        const unsigned co = (unsigned)(c0 + j) * uhw;
+                        const float top = topv[j] + (takes_up ? s_bot[j][tid - 32] : 0.f);
+                        atomicAdd(dsbb + (co + (unsigned)o00), top);
+                        if (bt.vy && !gives_down) atomicAdd(dsbb + (co + (unsigned)o10), botv[j]);
+                        if (!absorbed && bt.vx) {
+                            atomicAdd(dsbb + (co + (unsigned)o01), etop[j]);
+                            if (bt.vy) atomicAdd(dsbb + (co + (unsigned)o11), ebot[j]);
                         }
                     }
                 }
@@ -288,7 +323,7 @@ cudaError_t launch_feat_finalize(const FeatDev& p, cudaStream_t st) {
 }
 
 cudaError_t launch_feat_bwd(const FeatDev& p, cudaStream_t st) {
-    dim3 grid((unsigned)(((size_t)p.h * p.w + kFeatNT - 1) / kFeatNT), p.B);
+    dim3 grid((p.w + 31) / 32, (p.h + 3) / 4, p.B);
     if (p.d_tgt || p.d_src[0])
         feat_bwd_kernel<true><<<grid, kFeatNT, 0, st>>>(p);
     else
