@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define TDL_ABI_VERSION 1
+#define TDL_ABI_VERSION 2
 #define TDL_MAX_SRC 4      /* source frames per target (frame_ids[1:])       */
 #define TDL_MAX_SCALES 4   /* disparity scales (opt.scales)                  */
 
@@ -127,6 +127,11 @@ typedef struct tdl_feat_args {
     float* d_src[TDL_MAX_SRC];  /* out, optional (all or none), overwritten (zero where not selected)   */
     float* d_disp;              /* out (B,1,disp_h,disp_w), overwritten                                 */
     float* dP;                  /* out (B,S,3,4), overwritten                                           */
+    void* bwd_scratch;          /* optional, >= tdl_feat_bwd_scratch_bytes(): lets the d_src scatter of
+                                   grid_sample's backward run as a bucketed GATHER (no global atomics);
+                                   contents need not be preserved; NULL / too small / C % 4 != 0 =>
+                                   the atomic scatter kernel is used instead (same results)             */
+    uint64_t bwd_scratch_bytes;
 } tdl_feat_args;
 
 /* ------------------------------------------------------------------ edge-aware smoothness on C-channel maps */
@@ -184,6 +189,7 @@ int tdl_photo_fwd(const tdl_photo_args* args, tdl_stream_t stream);
 int tdl_photo_bwd(const tdl_photo_args* args, tdl_stream_t stream);
 
 uint64_t tdl_feat_ws_bytes(int32_t B, int32_t C, int32_t h, int32_t w, int32_t S);
+uint64_t tdl_feat_bwd_scratch_bytes(int32_t B, int32_t C, int32_t h, int32_t w, int32_t S);
 int tdl_feat_fwd(const tdl_feat_args* args, tdl_stream_t stream);
 int tdl_feat_bwd(const tdl_feat_args* args, tdl_stream_t stream);
 

@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol(lib, tdl):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/tdl.h but not exported by libtdl.so"
     assert sorted(tdl._lib.EXPORTS) == names
-    assert lib.tdl_abi_version() == 1
+    assert lib.tdl_abi_version() == 2
     assert lib.tdl_strerror(0) == b"ok"
     assert b"NULL" in lib.tdl_strerror(-1)
 

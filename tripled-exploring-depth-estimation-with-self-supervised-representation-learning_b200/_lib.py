@@ -6,11 +6,11 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtdl.so")
+LIB_PATH = os.environ.get("TDL_LIB_PATH") or os.path.join(HERE, "libtdl.so")   # override: kernel experiments only
 
 TDL_MAX_SRC = 4
 TDL_MAX_SCALES = 4
-TDL_ABI_VERSION = 1
+TDL_ABI_VERSION = 2
 
 _fp = C.POINTER(C.c_float)
 _vp = C.c_void_p
@@ -47,6 +47,7 @@ class FeatArgs(C.Structure):
         ("workspace", _vp), ("workspace_bytes", C.c_uint64),
         ("loss", _vp),
         ("dloss", _vp), ("d_tgt", _vp), ("d_src", _vp * TDL_MAX_SRC), ("d_disp", _vp), ("dP", _vp),
+        ("bwd_scratch", _vp), ("bwd_scratch_bytes", C.c_uint64),
     ]
 
 
@@ -75,7 +76,7 @@ class KernelTime(C.Structure):
 
 EXPORTS = ["tdl_abi_version", "tdl_strerror", "tdl_launch_count", "tdl_profile_begin", "tdl_profile_end",
            "tdl_photo_ws_bytes", "tdl_photo_fwd", "tdl_photo_bwd",
-           "tdl_feat_ws_bytes", "tdl_feat_fwd", "tdl_feat_bwd",
+           "tdl_feat_ws_bytes", "tdl_feat_bwd_scratch_bytes", "tdl_feat_fwd", "tdl_feat_bwd",
            "tdl_edge_ws_bytes", "tdl_edge_smooth_fwd", "tdl_edge_smooth_bwd",
            "tdl_recon_ws_bytes", "tdl_recon_fwd", "tdl_recon_bwd"]
 
@@ -107,6 +108,8 @@ def lib():
     L.tdl_photo_ws_bytes.argtypes = [C.c_int32] * 5 + [C.POINTER(C.c_int32)] * 2
     L.tdl_feat_ws_bytes.restype = C.c_uint64
     L.tdl_feat_ws_bytes.argtypes = [C.c_int32] * 5
+    L.tdl_feat_bwd_scratch_bytes.restype = C.c_uint64
+    L.tdl_feat_bwd_scratch_bytes.argtypes = [C.c_int32] * 5
     L.tdl_recon_ws_bytes.restype = C.c_uint64
     L.tdl_recon_ws_bytes.argtypes = []
     L.tdl_edge_ws_bytes.restype = C.c_uint64

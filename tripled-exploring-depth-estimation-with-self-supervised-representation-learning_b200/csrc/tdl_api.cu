@@ -192,7 +192,8 @@ int tdl_launch_count(const char* entry) {
     if (!strcmp(entry, "tdl_photo_fwd")) return 4;        // photo_warp + photo_score (or fused photo_fwd), smooth_fwd, finalize
     if (!strcmp(entry, "tdl_photo_bwd")) return 2;        // smooth_bwd, photo_bwd
     if (!strcmp(entry, "tdl_feat_fwd")) return 2;         // feat_fwd, finalize
-    if (!strcmp(entry, "tdl_feat_bwd")) return 1;
+    if (!strcmp(entry, "tdl_feat_bwd")) return 1;         // feat_bwd (atomic scatter / frozen features)
+    if (!strcmp(entry, "tdl_feat_bwd:gather")) return 3;  // feat_bwd (bucket) + feat_gather + feat_overflow (bwd_scratch given)
     if (!strcmp(entry, "tdl_edge_smooth_fwd")) return 3;  // area pyramid, smooth_fwd, finalize
     if (!strcmp(entry, "tdl_edge_smooth_bwd")) return 1;
     if (!strcmp(entry, "tdl_recon_fwd")) return 2;        // recon_fwd, finalize
@@ -280,6 +281,27 @@ uint64_t tdl_feat_ws_bytes(int32_t B, int32_t C, int32_t h, int32_t w, int32_t S
     return align_up((uint64_t)B * sizeof(double), 256) + align_up((uint64_t)B * h * w, 256);
 }
 
+// backward scratch of the bucketed d_src gather: [ov_cnt | bk_cnt] (zeroed per call) | bk_ent | ov_ent | G
+struct FeatScratchLayout {
+    uint64_t cnt_off, cnt_bytes, ent_off, ov_off, g_off, total;
+};
+static FeatScratchLayout feat_scratch_layout(int B, int C, int h, int w, int S) {
+    FeatScratchLayout L;
+    const uint64_t hw = (uint64_t)h * w;
+    L.cnt_off = 0;
+    L.cnt_bytes = align_up(256 + (uint64_t)S * B * hw * sizeof(int), 256);
+    L.ent_off = L.cnt_off + L.cnt_bytes;
+    L.ov_off = L.ent_off + align_up((uint64_t)S * B * hw * kFeatBucketCap * sizeof(int2), 256);
+    L.g_off = L.ov_off + align_up(4 * (uint64_t)B * hw * sizeof(int4), 256);
+    L.total = L.g_off + align_up((uint64_t)B * hw * C * sizeof(float), 256);
+    return L;
+}
+
+uint64_t tdl_feat_bwd_scratch_bytes(int32_t B, int32_t C, int32_t h, int32_t w, int32_t S) {
+    if (B < 1 || C < 1 || h < 1 || w < 1 || S < 1 || S > TDL_MAX_SRC) return 0;
+    return feat_scratch_layout(B, C, h, w, S).total;
+}
+
 static int check_feat(const tdl_feat_args* a, bool bwd, FeatDev* d) {
     if (!a) return TDL_ERR_NULL;
     if (a->S < 1 || a->S > TDL_MAX_SRC || a->C < 1) return TDL_ERR_COUNT;
@@ -313,6 +335,16 @@ static int check_feat(const tdl_feat_args* a, bool bwd, FeatDev* d) {
     if (bwd) {
         if (!a->dloss || !a->d_disp || !a->dP) return TDL_ERR_NULL;
         d->dloss = a->dloss; d->d_tgt = a->d_tgt; d->d_disp = a->d_disp; d->dP = a->dP;
+        const FeatScratchLayout L = feat_scratch_layout(a->B, a->C, a->h, a->w, a->S);
+        if (n_dsrc == a->S && a->bwd_scratch && a->bwd_scratch_bytes >= L.total && a->C % 4 == 0 &&
+            (reinterpret_cast<uintptr_t>(a->bwd_scratch) & 15) == 0 && getenv("TDL_FEAT_ATOMIC") == nullptr) {
+            char* sc = static_cast<char*>(a->bwd_scratch);
+            d->ov_cnt = reinterpret_cast<int*>(sc + L.cnt_off);
+            d->bk_cnt = reinterpret_cast<int*>(sc + L.cnt_off + 256);
+            d->bk_ent = reinterpret_cast<int2*>(sc + L.ent_off);
+            d->ov_ent = reinterpret_cast<int4*>(sc + L.ov_off);
+            d->G = reinterpret_cast<float*>(sc + L.g_off);
+        }
     }
     return TDL_OK;
 }
@@ -337,6 +369,14 @@ int tdl_feat_bwd(const tdl_feat_args* a, tdl_stream_t stream) {
     TDL_KERNEL("memset", cudaMemsetAsync(a->dP, 0, (size_t)a->B * a->S * 12 * sizeof(float), st));
     if (a->disp_h != a->h || a->disp_w != a->w)
         TDL_KERNEL("memset", cudaMemsetAsync(a->d_disp, 0, (size_t)a->B * a->disp_h * a->disp_w * sizeof(float), st));
+    if (d.G) {       // bucketed gather: per-pixel kernel registers taps + writes G, gather kernel writes d_src (no memset)
+        const FeatScratchLayout L = feat_scratch_layout(a->B, a->C, a->h, a->w, a->S);
+        TDL_KERNEL("memset", cudaMemsetAsync(d.ov_cnt, 0, L.cnt_bytes, st));
+        TDL_KERNEL("feat_bwd", launch_feat_bwd(d, st));
+        TDL_KERNEL("feat_gather", launch_feat_bwd_gather(d, st));
+        TDL_KERNEL("feat_overflow", launch_feat_bwd_overflow(d, st));
+        return TDL_OK;
+    }
     for (int f = 0; f < a->S; ++f)
         if (a->d_src[f]) TDL_KERNEL("memset_dsrc", cudaMemsetAsync(a->d_src[f], 0, fbytes, st));
     TDL_KERNEL("feat_bwd", launch_feat_bwd(d, st));

@@ -8,6 +8,7 @@
 // the C channels are streamed: lanes hold consecutive x, so the target reads and the
 // warped-feature writes are fully coalesced and the 4-tap gathers hit neighbouring lines.
 // HBM-bound: (1 + S) * C * 4 B read + S * C * 4 B written per pixel in the forward.
+#include <stdio.h>
 #include "tdl_common.cuh"
 #include "tdl_internal.h"
 
@@ -305,6 +306,294 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
     if (tid < S * 12 && s_dP[tid] != 0.f) atomicAdd(p.dP + (size_t)b * S * 12 + tid, s_dP[tid]);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward with trainable features, bucketed: grid_sample's d_src scatter as a GATHER.
+//
+// The scatter pattern (which source pixels a target pixel touches, with which bilinear weights) is the same for all C
+// channels, and a global reduction costs ~1.3 issue cycles per LANE on B200 (REDG, spread addresses) -- 2..4 of them per
+// pixel and channel bounded the atomic kernel above at ~150 us for the bench shape.  Here the per-pixel kernel
+//   * writes g[c] = d loss / d warped value channel-LAST into G[b][pixel][C] (one 16-byte store per 4 channels), and
+//   * registers its (up to) four taps in the bucket of the source pixel they touch: (target pixel, weight), one integer
+//     atomic per tap instead of one float reduction per tap AND channel;
+// then feat_gather_kernel walks the source pixels: 16 lanes x float4 = 64 channels read the G rows of the registered taps
+// (256 contiguous bytes each), accumulate in registers, and the CTA writes the NCHW d_src tile through a shared-memory
+// transpose with full 128-byte lines -- no memset of d_src, no float atomics.  Buckets hold kFeatBucketCap taps; the rare
+// excess goes to an overflow list that feat_overflow_kernel adds with atomics afterwards.
+__global__ void __launch_bounds__(kFeatNT) feat_bwd_bucket_kernel(const FeatDev p) {
+    __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
+    __shared__ float s_dP[TDL_MAX_SRC * 12];
+    const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5;
+    const int b = blockIdx.z;
+    const int h = p.h, w = p.w, C = p.C, S = p.S;
+    const size_t hw = (size_t)h * w;
+    if (tid < S * 12) {
+        s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
+        s_dP[tid] = 0.f;
+    }
+    if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
+    __syncthreads();
+    const int xq = blockIdx.x * 32 + lane, yq = blockIdx.y * 4 + wr;
+    const bool active = xq < w && yq < h;
+    const int y = active ? yq : 0, x = active ? xq : 0;
+    const int pix = y * w + x;
+    const int fsel = active ? p.argmin[(size_t)b * hw + pix] : -1;
+    const DepthParams dp{p.min_disp, p.range};
+    const UpTap ut = up_tap(y, x, p.sy, p.sx, p.dh, p.dw);
+    const Geo g = backproject(up_value(p.disp + (size_t)b * p.dh * p.dw, p.dw, ut), dp, s_cam + TDL_MAX_SRC * 12, x, y);
+    const float* Pf = s_cam + max(fsel, 0) * 12;
+    const Proj pr = project<true>(g, Pf, h, w, p.align_corners);
+    const Bilin bt = bilin_taps(pr.ix, pr.iy, h, w);
+    const float up = active ? __ldg(p.dloss) * p.coef / ((float)p.B * (float)h * (float)w) / (float)C : 0.f;
+    const float* sb = p.src[0];
+#pragma unroll
+    for (int f = 1; f < TDL_MAX_SRC; ++f)
+        if (f == fsel) sb = p.src[f];
+    const int x1 = min(bt.x0 + 1, w - 1), y1 = min(bt.y0 + 1, h - 1);
+    const int o00 = bt.y0 * w + bt.x0, o01 = bt.y0 * w + x1, o10 = y1 * w + bt.x0, o11 = y1 * w + x1;
+
+#ifndef TDL_X_NOREG
+    if (active) {                                            // register the taps (channel independent)
+        const int fb = fsel * p.B + b;
+        int* cnt = p.bk_cnt + (size_t)fb * hw;
+        int2* ent = p.bk_ent + (size_t)fb * hw * kFeatBucketCap;
+        auto reg = [&](int o, float wgt) {
+            if (wgt != 0.f) {                                // a zero weight contributes exactly 0
+                const int slot = atomicAdd(cnt + o, 1);
+                if (slot < kFeatBucketCap) {
+                    ent[(size_t)o * kFeatBucketCap + slot] = make_int2(pix, __float_as_int(wgt));
+                } else {
+const int k = atomicAdd(p.ov_cnt, 1);      // (warp-aggregating this counter measured 38 us SLOWER)
+                    p.ov_ent[k] = make_int4(fb, o, pix, __float_as_int(wgt));
+                }
+            }
+        };
+        reg(o00, bt.nw);
+        if (bt.vx) reg(o01, bt.ne);
+        if (bt.vy) reg(o10, bt.sw);
+        if (bt.vx && bt.vy) reg(o11, bt.se);
+    }
+#endif
+
+    constexpr int CB = 4;                                    // == the float4 written to G; C % 4 == 0 on this path
+    const unsigned uhw = (unsigned)hw, upix = (unsigned)pix;
+    const float* tbase = p.tgt + (size_t)b * C * hw;
+    const float* sbb = sb + (size_t)b * C * hw;
+    float* dtb = p.d_tgt ? p.d_tgt + (size_t)b * C * hw : nullptr;
+    float* Gp = p.G + ((size_t)b * hw + pix) * C;
+    float gix = 0.f, giy = 0.f;
+    for (int c0 = 0; c0 < C; c0 += CB) {
+        float t[CB], v[CB][4];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+            const unsigned co = (unsigned)(c0 + j) * uhw;
+            t[j] = active ? __ldg(tbase + (co + upix)) : 0.f;
+            v[j][0] = active ? __ldg(sbb + (co + (unsigned)o00)) : 0.f;
+            v[j][1] = active ? __ldg(sbb + (co + (unsigned)o01)) : 0.f;
+            v[j][2] = active ? __ldg(sbb + (co + (unsigned)o10)) : 0.f;
+            v[j][3] = active ? __ldg(sbb + (co + (unsigned)o11)) : 0.f;
+        }
+        float gq[CB];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+            const unsigned co = (unsigned)(c0 + j) * uhw;
+            const float v00 = v[j][0], v01 = bt.vx ? v[j][1] : 0.f, v10 = bt.vy ? v[j][2] : 0.f;
+            const float v11 = (bt.vx && bt.vy) ? v[j][3] : 0.f;
+            const float val = v00 * bt.nw + v01 * bt.ne + v10 * bt.sw + v11 * bt.se;
+            const float dix = -v00 * bt.ey + v01 * bt.ey - v10 * bt.ay + v11 * bt.ay;
+            const float diy = -v00 * bt.ex - v01 * bt.ax + v10 * bt.ex + v11 * bt.ax;
+            const float df = val - t[j];
+            const float gvv = up * df * rsqrt_approx(df * df + kL1Eps2);      // d loss / d warped value
+            gix += gvv * dix;
+            giy += gvv * diy;
+            gq[j] = gvv;
+            if (dtb && active) dtb[co + upix] = -gvv;
+        }
+#ifndef TDL_X_NOG
+        if (active) *reinterpret_cast<float4*>(Gp + c0) = make_float4(gq[0], gq[1], gq[2], gq[3]);
+#endif
+    }
+    float aP[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) aP[k] = 0.f;
+    if (active) {
+        const float gu = gix * pr.mx, gv = giy * pr.my;
+        const float rz = __frcp_rn(pr.z);
+        const float gp0 = gu * rz, gp1 = gv * rz, gp2 = -(gu * pr.u + gv * pr.v) * rz;
+        aP[0] = gp0 * g.X0; aP[1] = gp0 * g.X1; aP[2] = gp0 * g.X2; aP[3] = gp0;
+        aP[4] = gp1 * g.X0; aP[5] = gp1 * g.X1; aP[6] = gp1 * g.X2; aP[7] = gp1;
+        aP[8] = gp2 * g.X0; aP[9] = gp2 * g.X1; aP[10] = gp2 * g.X2; aP[11] = gp2;
+        const float gX0 = Pf[0] * gp0 + Pf[4] * gp1 + Pf[8] * gp2;
+        const float gX1 = Pf[1] * gp0 + Pf[5] * gp1 + Pf[9] * gp2;
+        const float gX2 = Pf[2] * gp0 + Pf[6] * gp1 + Pf[10] * gp2;
+        const float gD = gX0 * g.r0 + gX1 * g.r1 + gX2 * g.r2;
+        const float gdisp = -p.range * g.D * g.D * gD;
+        float* dd = p.d_disp + (size_t)b * p.dh * p.dw;
+        if (p.dh == h && p.dw == w) {
+            dd[pix] = gdisp;
+        } else {
+            const float hy = 1.f - ut.ly, hx = 1.f - ut.lx;
+            atomicAdd(dd + (size_t)ut.y0 * p.dw + ut.x0, hy * hx * gdisp);
+            atomicAdd(dd + (size_t)ut.y0 * p.dw + ut.x1, hy * ut.lx * gdisp);
+            atomicAdd(dd + (size_t)ut.y1 * p.dw + ut.x0, ut.ly * hx * gdisp);
+            atomicAdd(dd + (size_t)ut.y1 * p.dw + ut.x1, ut.ly * ut.lx * gdisp);
+        }
+    }
+    for (int f = 0; f < S; ++f) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const float v = warp_sum((active && f == fsel) ? aP[k] : 0.f);
+            if (lane == 0 && v != 0.f) atomicAdd(&s_dP[f * 12 + k], v);
+        }
+    }
+    __syncthreads();
+    if (tid < S * 12 && s_dP[tid] != 0.f) atomicAdd(p.dP + (size_t)b * S * 12 + tid, s_dP[tid]);
+}
+
+constexpr int kGatherWarps = 4;     // warps per CTA; every warp owns one tile and never synchronises with the others
+constexpr int kGatherPix = 32;      // source pixels (consecutive in the plane) per tile = one 128-byte line per channel
+constexpr int kGatherBatch = 32;    // G rows in flight per warp
+
+// One WARP per tile of 32 consecutive source pixels, no CTA-level synchronisation.
+//   1. lane L reads the bucket (size + 8 entries, 4 x 16 B) of pixel o0+L; a warp scan compacts the registered taps of
+//      the tile into a shared list (pixel-in-tile, target pixel, weight) -- ~64 taps per tile for the bench's flow;
+//   2. the list is walked in batches of kGatherBatch taps: for every tap the 32 lanes read one G row (64 channels = 256
+//      contiguous bytes, float2 per lane), all loads of a batch in flight before the first use;
+//   3. each row is accumulated into the per-warp shared tile [channel][pixel] (the tap's pixel index is dynamic, so the
+//      accumulators cannot live in registers); the tile leaves as 64 full 128-byte lines of the NCHW gradient.
+__global__ void __launch_bounds__(kGatherWarps * 32) feat_gather_kernel(const FeatDev p) {
+    __shared__ float s_t[kGatherWarps][64 * (kGatherPix + 1)];
+    __shared__ int2 s_l[kGatherWarps][kGatherPix * kFeatBucketCap];     // .x = target pixel | pixel-in-tile << 26 ... see below
+    __shared__ unsigned char s_q[kGatherWarps][kGatherPix * kFeatBucketCap];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int fb = blockIdx.y;                               // frame * B + b
+    const int f = fb / p.B, b = fb - f * p.B;
+    const int hw = p.h * p.w, C = p.C;
+    const int o0 = (blockIdx.x * kGatherWarps + wq) * kGatherPix;
+    if (o0 >= hw) return;
+    float* dst = p.d_src[0];
+#pragma unroll
+    for (int k = 1; k < TDL_MAX_SRC; ++k)
+        if (k == f) dst = p.d_src[k];
+    dst += (size_t)b * C * hw;
+    const float* Gb = p.G + (size_t)b * hw * C;
+    float* st = s_t[wq];
+    int2* sl = s_l[wq];
+    unsigned char* sq = s_q[wq];
+    // 1. my pixel's bucket -> compact list (row offset into G, weight) + the tap's pixel-in-tile
+    const int o = min(o0 + lane, hw - 1);
+    const int4* e4 = reinterpret_cast<const int4*>(p.bk_ent + ((size_t)fb * hw + o) * kFeatBucketCap);
+    const int n = (o0 + lane < hw) ? min(__ldg(p.bk_cnt + (size_t)fb * hw + o), kFeatBucketCap) : 0;
+    int4 e[kFeatBucketCap / 2];
+#pragma unroll
+    for (int k = 0; k < kFeatBucketCap / 2; ++k) e[k] = __ldg(e4 + k);
+    int off = n;                                             // inclusive scan
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, off, d);
+        if (lane >= d) off += v;
+    }
+    const int T = __shfl_sync(0xffffffffu, off, 31);
+    const unsigned empty = __ballot_sync(0xffffffffu, n == 0);
+    off -= n;
+#pragma unroll
+    for (int k = 0; k < kFeatBucketCap / 2; ++k) {
+        if (2 * k < n) {
+            sl[off + 2 * k] = make_int2(e[k].x * C, e[k].y);
+            sq[off + 2 * k] = (unsigned char)lane;
+        }
+        if (2 * k + 1 < n) {
+            sl[off + 2 * k + 1] = make_int2(e[k].z * C, e[k].w);
+            sq[off + 2 * k + 1] = (unsigned char)lane;
+        }
+    }
+    const unsigned uhw = (unsigned)hw;
+    for (int cc = 0; cc < C; cc += 64) {
+        const int c = min(cc + 2 * lane, C - 2);             // lanes past C redo the last pair (not stored)
+        const float* Gc = Gb + c;
+        float* col = st + (2 * lane) * (kGatherPix + 1);     // my two channel rows of the tile
+        __syncwarp();                                        // list written / previous chunk's lines read
+        for (unsigned m = empty; m; m &= m - 1) {            // pixels without taps
+            const int q = __ffs(m) - 1;
+            col[q] = 0.f;
+            col[kGatherPix + 1 + q] = 0.f;
+        }
+        // 2./3. the taps of one pixel are consecutive in the list: accumulate in registers, store at every pixel change
+        float2 acc = make_float2(0.f, 0.f);
+        int cur = T > 0 ? sq[0] : 0;
+        for (int t0 = 0; t0 < T; t0 += kGatherBatch) {
+            float2 g2[kGatherBatch];
+#pragma unroll
+            for (int k = 0; k < kGatherBatch; ++k) {
+                const int t = min(t0 + k, T - 1);            // past the end: re-read the last row (L1 hit), not accumulated
+                g2[k] = __ldg(reinterpret_cast<const float2*>(Gc + (unsigned)sl[t].x));
+            }
+#pragma unroll
+            for (int k = 0; k < kGatherBatch; ++k) {
+                if (t0 + k < T) {                            // warp-uniform
+                    const int q = sq[t0 + k];
+                    if (q != cur) {                          // warp-uniform
+                        col[cur] = acc.x;
+                        col[kGatherPix + 1 + cur] = acc.y;
+                        acc = make_float2(0.f, 0.f);
+                        cur = q;
+                    }
+                    const float wgt = __int_as_float(sl[t0 + k].y);
+                    acc.x = fmaf(wgt, g2[k].x, acc.x);
+                    acc.y = fmaf(wgt, g2[k].y, acc.y);
+                }
+            }
+        }
+        if (T > 0) {
+            col[cur] = acc.x;
+            col[kGatherPix + 1 + cur] = acc.y;
+        }
+        __syncwarp();
+        if (o0 + lane < hw) {
+            const int nch = min(64, C - cc);
+            float* d0 = dst + (size_t)cc * hw + o0 + lane;
+            const float* s0 = st + lane;
+            int ch = 0;
+            for (; ch + 8 <= nch; ch += 8) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = s0[(ch + j) * (kGatherPix + 1)];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d0[(unsigned)(ch + j) * uhw] = v[j];
+            }
+            for (; ch < nch; ++ch) d0[(unsigned)ch * uhw] = s0[ch * (kGatherPix + 1)];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) feat_overflow_kernel(const FeatDev p) {
+    const int n = *p.ov_cnt;
+#ifdef TDL_DEBUG_OV
+    if (blockIdx.x == 0 && threadIdx.x == 0) printf("feat overflow entries: %d\n", n);
+#endif
+    const int ngrp = (int)(gridDim.x * blockDim.x) >> 4;
+    const int l16 = threadIdx.x & 15;
+    const int hw = p.h * p.w, C = p.C;
+    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) >> 4; i < n; i += ngrp) {
+        const int4 e = p.ov_ent[i];
+        const int f = e.x / p.B, b = e.x - f * p.B;
+        float* dst = p.d_src[0];
+#pragma unroll
+        for (int k = 1; k < TDL_MAX_SRC; ++k)
+            if (k == f) dst = p.d_src[k];
+        dst += (size_t)b * C * hw + e.y;
+        const float wgt = __int_as_float(e.w);
+        const float* Gr = p.G + ((size_t)b * hw + e.z) * C;
+        for (int c = 4 * l16; c < C; c += 64) {
+            const float4 gv = *reinterpret_cast<const float4*>(Gr + c);
+            atomicAdd(dst + (size_t)(c + 0) * hw, wgt * gv.x);
+            atomicAdd(dst + (size_t)(c + 1) * hw, wgt * gv.y);
+            atomicAdd(dst + (size_t)(c + 2) * hw, wgt * gv.z);
+            atomicAdd(dst + (size_t)(c + 3) * hw, wgt * gv.w);
+        }
+    }
+}
+
 cudaError_t launch_feat_fwd(const FeatDev& p, cudaStream_t st) {
     dim3 grid((unsigned)(((size_t)p.h * p.w + kFeatNT - 1) / kFeatNT), p.B);
     switch (p.S) {
@@ -324,10 +613,24 @@ cudaError_t launch_feat_finalize(const FeatDev& p, cudaStream_t st) {
 
 cudaError_t launch_feat_bwd(const FeatDev& p, cudaStream_t st) {
     dim3 grid((p.w + 31) / 32, (p.h + 3) / 4, p.B);
-    if (p.d_tgt || p.d_src[0])
+    if (p.G)
+        feat_bwd_bucket_kernel<<<grid, kFeatNT, 0, st>>>(p);
+    else if (p.d_tgt || p.d_src[0])
         feat_bwd_kernel<true><<<grid, kFeatNT, 0, st>>>(p);
     else
         feat_bwd_kernel<false><<<grid, kFeatNT, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_feat_bwd_gather(const FeatDev& p, cudaStream_t st) {
+    const int tiles = (p.h * p.w + kGatherPix - 1) / kGatherPix;
+    dim3 grid((tiles + kGatherWarps - 1) / kGatherWarps, p.S * p.B);
+    feat_gather_kernel<<<grid, kGatherWarps * 32, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_feat_bwd_overflow(const FeatDev& p, cudaStream_t st) {
+    feat_overflow_kernel<<<148 * 8, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -87,7 +87,14 @@ struct FeatDev {
     float* d_src[TDL_MAX_SRC];
     float* d_disp;
     float* dP;
+    // bucketed d_src gather (backward scratch; all null when the atomic scatter kernel is to be used)
+    float* G;                    // [B][h*w][C]  d loss / d warped value, channel-last
+    int* bk_cnt;                 // [S][B][h*w]  taps registered per source pixel
+    int2* bk_ent;                // [S][B][h*w][kFeatBucketCap]  (target pixel, weight bits)
+    int* ov_cnt;                 // [1]          length of the overflow list
+    int4* ov_ent;                // [4*B*h*w]    (frame*B + b, source pixel, target pixel, weight bits)
 };
+constexpr int kFeatBucketCap = 8;
 
 // ---- masked image-reconstruction loss (TripleD family) ----------------------------------------------------
 struct ReconArgsDev {
@@ -118,6 +125,8 @@ cudaError_t launch_photo_finalize(const PhotoDev& p, const float* photo_coef, co
 cudaError_t launch_feat_fwd(const FeatDev& p, cudaStream_t st);
 cudaError_t launch_feat_finalize(const FeatDev& p, cudaStream_t st);
 cudaError_t launch_feat_bwd(const FeatDev& p, cudaStream_t st);
+cudaError_t launch_feat_bwd_gather(const FeatDev& p, cudaStream_t st);      // after launch_feat_bwd when p.G != nullptr
+cudaError_t launch_feat_bwd_overflow(const FeatDev& p, cudaStream_t st);    // after the gather
 cudaError_t launch_edge_finalize(const double* acc, int acc_stride, int B, float first_coef, float second_coef,
                                  int h, int w, float* loss, cudaStream_t st);
 

@@ -262,6 +262,11 @@ class FeatureMetricLoss(torch.autograd.Function):
             d_srcs = [torch.empty_like(tgt) for _ in range(S)]
             for f, t in enumerate(d_srcs):
                 a.d_src[f] = t.data_ptr()
+            # scratch of the bucketed d_src gather (lives for this call only; the library falls back to its
+            # atomic scatter kernel when C % 4 != 0)
+            sc_bytes = L.tdl_feat_bwd_scratch_bytes(B, Cc, h, w, S)
+            scratch_buf = torch.empty(sc_bytes, dtype=torch.uint8, device=tgt.device)
+            a.bwd_scratch, a.bwd_scratch_bytes = scratch_buf.data_ptr(), sc_bytes
         with torch.cuda.device(tgt.device):
             _lib.check(L.tdl_feat_bwd(C.byref(a), _stream()), "tdl_feat_bwd")
         return (None, d_tgt, d_disp, dP, None, *d_srcs)
