@@ -336,7 +336,7 @@ static int check_feat(const tdl_feat_args* a, bool bwd, FeatDev* d) {
         if (!a->dloss || !a->d_disp || !a->dP) return TDL_ERR_NULL;
         d->dloss = a->dloss; d->d_tgt = a->d_tgt; d->d_disp = a->d_disp; d->dP = a->dP;
         const FeatScratchLayout L = feat_scratch_layout(a->B, a->C, a->h, a->w, a->S);
-        if (n_dsrc == a->S && a->bwd_scratch && a->bwd_scratch_bytes >= L.total && a->C % 4 == 0 &&
+        if (n_dsrc == a->S && a->bwd_scratch && a->bwd_scratch_bytes >= L.total && a->C % 4 == 0 && (uint64_t)a->h * a->w * a->C < (1ull << 28) &&
             (reinterpret_cast<uintptr_t>(a->bwd_scratch) & 15) == 0 && getenv("TDL_FEAT_ATOMIC") == nullptr) {
             char* sc = static_cast<char*>(a->bwd_scratch);
             d->ov_cnt = reinterpret_cast<int*>(sc + L.cnt_off);

@@ -452,20 +452,25 @@ const int k = atomicAdd(p.ov_cnt, 1);      // (warp-aggregating this counter mea
 
 constexpr int kGatherWarps = 4;     // warps per CTA; every warp owns one tile and never synchronises with the others
 constexpr int kGatherPix = 32;      // source pixels (consecutive in the plane) per tile = one 128-byte line per channel
-constexpr int kGatherBatch = 32;    // G rows in flight per warp
+constexpr int kGatherBatch = 8;     // pipeline depth in steps; a step = one G row per HALF-warp, i.e. 16 rows in flight per warp
+constexpr int kGatherSub = 16 * kFeatBucketCap + kGatherBatch;   // list capacity of a half-warp (16 pixels) + read-ahead padding
 
-// One WARP per tile of 32 consecutive source pixels, no CTA-level synchronisation.
-//   1. lane L reads the bucket (size + 8 entries, 4 x 16 B) of pixel o0+L; a warp scan compacts the registered taps of
-//      the tile into a shared list (pixel-in-tile, target pixel, weight) -- ~64 taps per tile for the bench's flow;
-//   2. the list is walked in batches of kGatherBatch taps: for every tap the 32 lanes read one G row (64 channels = 256
-//      contiguous bytes, float2 per lane), all loads of a batch in flight before the first use;
-//   3. each row is accumulated into the per-warp shared tile [channel][pixel] (the tap's pixel index is dynamic, so the
-//      accumulators cannot live in registers); the tile leaves as 64 full 128-byte lines of the NCHW gradient.
+// One WARP per tile of 32 consecutive source pixels, no CTA-level synchronisation.  ncu (profiles/) shows this kernel bound by
+// L1/shared-memory wavefronts (82 % busy in its first version), so every shared-memory access below is conflict-free and
+// the per-tap list entry is ONE 8-byte word.
+//   1. lane L reads the bucket (size + 8 entries, 4 x 16 B) of pixel o0+L; a warp scan compacts the registered taps
+//      into two shared lists (pixels 0-15 / 16-31 of the tile).  Entry = (G row offset in 16-byte units << 5 | last-tap
+//      flag << 4 | pixel-in-half, weight); lists are padded with zero-weight taps to a common multiple of the depth;
+//   2. each half-warp walks its list: 16 lanes x float4 read one G row (64 channels = 256 contiguous bytes) per step
+//      through a software pipeline of depth kGatherBatch;
+//   3. the taps of a pixel are consecutive: they accumulate in registers and go to the per-warp shared tile at the pixel's
+//      last tap.  Tile cell (channel c, pixel q) lives at word c*32 + (q ^ (c >> 2)): the writes (16 lanes = 16 channel
+//      quads, fixed q) and the reads (32 lanes = 32 pixels, fixed c) both touch 32 distinct banks;
+//   4. the tile leaves as 64 full 128-byte lines of the NCHW gradient.
 __global__ void __launch_bounds__(kGatherWarps * 32) feat_gather_kernel(const FeatDev p) {
-    __shared__ float s_t[kGatherWarps][64 * (kGatherPix + 1)];
-    __shared__ int2 s_l[kGatherWarps][kGatherPix * kFeatBucketCap];     // .x = target pixel | pixel-in-tile << 26 ... see below
-    __shared__ unsigned char s_q[kGatherWarps][kGatherPix * kFeatBucketCap];
-    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    __shared__ float s_t[kGatherWarps][64 * kGatherPix];
+    __shared__ int2 s_l[kGatherWarps][2 * kGatherSub];
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15;
     const int fb = blockIdx.y;                               // frame * B + b
     const int f = fb / p.B, b = fb - f * p.B;
     const int hw = p.h * p.w, C = p.C;
@@ -476,92 +481,92 @@ __global__ void __launch_bounds__(kGatherWarps * 32) feat_gather_kernel(const Fe
     for (int k = 1; k < TDL_MAX_SRC; ++k)
         if (k == f) dst = p.d_src[k];
     dst += (size_t)b * C * hw;
-    const float* Gb = p.G + (size_t)b * hw * C;
+    const float4* Gb = reinterpret_cast<const float4*>(p.G + (size_t)b * hw * C);
     float* st = s_t[wq];
-    int2* sl = s_l[wq];
-    unsigned char* sq = s_q[wq];
-    // 1. my pixel's bucket -> compact list (row offset into G, weight) + the tap's pixel-in-tile
+    int2* sl = s_l[wq] + half * kGatherSub;
+    // 1. my pixel's bucket -> my half's list
     const int o = min(o0 + lane, hw - 1);
     const int4* e4 = reinterpret_cast<const int4*>(p.bk_ent + ((size_t)fb * hw + o) * kFeatBucketCap);
     const int n = (o0 + lane < hw) ? min(__ldg(p.bk_cnt + (size_t)fb * hw + o), kFeatBucketCap) : 0;
     int4 e[kFeatBucketCap / 2];
 #pragma unroll
     for (int k = 0; k < kFeatBucketCap / 2; ++k) e[k] = __ldg(e4 + k);
-    int off = n;                                             // inclusive scan
+    int off = n;                                             // inclusive scan inside each half
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
+    for (int d = 1; d < 16; d <<= 1) {
         const int v = __shfl_up_sync(0xffffffffu, off, d);
-        if (lane >= d) off += v;
+        if (l16 >= d) off += v;
     }
-    const int T = __shfl_sync(0xffffffffu, off, 31);
+    const int Th = __shfl_sync(0xffffffffu, off, 15, 16);    // taps of my half
+    const int Tmax = max(__shfl_sync(0xffffffffu, Th, 0), __shfl_sync(0xffffffffu, Th, 16));
+    const int Tpad = (Tmax + kGatherBatch - 1) / kGatherBatch * kGatherBatch;
     const unsigned empty = __ballot_sync(0xffffffffu, n == 0);
     off -= n;
+    const int row16 = C >> 2;                                // G row length in 16-byte units
 #pragma unroll
     for (int k = 0; k < kFeatBucketCap / 2; ++k) {
-        if (2 * k < n) {
-            sl[off + 2 * k] = make_int2(e[k].x * C, e[k].y);
-            sq[off + 2 * k] = (unsigned char)lane;
-        }
-        if (2 * k + 1 < n) {
-            sl[off + 2 * k + 1] = make_int2(e[k].z * C, e[k].w);
-            sq[off + 2 * k + 1] = (unsigned char)lane;
-        }
+        if (2 * k < n) sl[off + 2 * k] = make_int2(((e[k].x * row16) << 5) | (2 * k == n - 1 ? 16 : 0) | l16, e[k].y);
+        if (2 * k + 1 < n) sl[off + 2 * k + 1] = make_int2(((e[k].z * row16) << 5) | (2 * k + 1 == n - 1 ? 16 : 0) | l16, e[k].w);
     }
+    for (int t = Th + l16; t < Tpad + kGatherBatch; t += 16) sl[t] = make_int2(0, 0);   // padding + read-ahead: row 0, weight 0
     const unsigned uhw = (unsigned)hw;
     for (int cc = 0; cc < C; cc += 64) {
-        const int c = min(cc + 2 * lane, C - 2);             // lanes past C redo the last pair (not stored)
-        const float* Gc = Gb + c;
-        float* col = st + (2 * lane) * (kGatherPix + 1);     // my two channel rows of the tile
-        __syncwarp();                                        // list written / previous chunk's lines read
+        const int c = min(cc + 4 * l16, C - 4);              // lanes past C redo the last quad (not stored)
+        const float4* Gc = Gb + (c >> 2);
+        float* col = st + (4 * l16) * kGatherPix;            // my four channel rows of the tile; (4*l16 + j) >> 2 == l16
+        __syncwarp();                                        // lists written / previous chunk's lines read
         for (unsigned m = empty; m; m &= m - 1) {            // pixels without taps
             const int q = __ffs(m) - 1;
-            col[q] = 0.f;
-            col[kGatherPix + 1 + q] = 0.f;
-        }
-        // 2./3. the taps of one pixel are consecutive in the list: accumulate in registers, store at every pixel change
-        float2 acc = make_float2(0.f, 0.f);
-        int cur = T > 0 ? sq[0] : 0;
-        for (int t0 = 0; t0 < T; t0 += kGatherBatch) {
-            float2 g2[kGatherBatch];
+            if ((q >> 4) == half) {
 #pragma unroll
-            for (int k = 0; k < kGatherBatch; ++k) {
-                const int t = min(t0 + k, T - 1);            // past the end: re-read the last row (L1 hit), not accumulated
-                g2[k] = __ldg(reinterpret_cast<const float2*>(Gc + (unsigned)sl[t].x));
+                for (int j = 0; j < 4; ++j) col[j * kGatherPix + (q ^ l16)] = 0.f;
             }
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int2 ev[kGatherBatch];
+        float4 g4[kGatherBatch];
+#pragma unroll
+        for (int k = 0; k < kGatherBatch; ++k) {
+            ev[k] = sl[k];
+            g4[k] = __ldg(Gc + ((unsigned)ev[k].x >> 5));
+        }
+        for (int t0 = 0; t0 < Tpad; t0 += kGatherBatch) {
 #pragma unroll
             for (int k = 0; k < kGatherBatch; ++k) {
-                if (t0 + k < T) {                            // warp-uniform
-                    const int q = sq[t0 + k];
-                    if (q != cur) {                          // warp-uniform
-                        col[cur] = acc.x;
-                        col[kGatherPix + 1 + cur] = acc.y;
-                        acc = make_float2(0.f, 0.f);
-                        cur = q;
-                    }
-                    const float wgt = __int_as_float(sl[t0 + k].y);
-                    acc.x = fmaf(wgt, g2[k].x, acc.x);
-                    acc.y = fmaf(wgt, g2[k].y, acc.y);
+                const float wgt = __int_as_float(ev[k].y);
+                const int meta = ev[k].x;
+                acc.x = fmaf(wgt, g4[k].x, acc.x);
+                acc.y = fmaf(wgt, g4[k].y, acc.y);
+                acc.z = fmaf(wgt, g4[k].z, acc.z);
+                acc.w = fmaf(wgt, g4[k].w, acc.w);
+                ev[k] = sl[t0 + kGatherBatch + k];
+                g4[k] = __ldg(Gc + ((unsigned)ev[k].x >> 5));
+                if (meta & 16) {                             // last tap of pixel half*16 + (meta & 15): uniform in the half-warp
+                    float* cq = col + ((half * 16 + (meta & 15)) ^ l16);
+                    cq[0] = acc.x;
+                    cq[kGatherPix] = acc.y;
+                    cq[2 * kGatherPix] = acc.z;
+                    cq[3 * kGatherPix] = acc.w;
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
-        }
-        if (T > 0) {
-            col[cur] = acc.x;
-            col[kGatherPix + 1 + cur] = acc.y;
         }
         __syncwarp();
         if (o0 + lane < hw) {
             const int nch = min(64, C - cc);
             float* d0 = dst + (size_t)cc * hw + o0 + lane;
-            const float* s0 = st + lane;
             int ch = 0;
-            for (; ch + 8 <= nch; ch += 8) {
+            for (; ch + 8 <= nch; ch += 8) {                 // ch % 4 == 0: the two quads of this group are ch>>2 and (ch>>2)+1
                 float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = s0[(ch + j) * (kGatherPix + 1)];
+                for (int j = 0; j < 8; ++j) v[j] = st[(ch + j) * kGatherPix + (lane ^ ((ch + j) >> 2))];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) d0[(unsigned)(ch + j) * uhw] = v[j];
+                for (int j = 0; j < 8; ++j) {
+                    *d0 = v[j];
+                    d0 += uhw;
+                }
             }
-            for (; ch < nch; ++ch) d0[(unsigned)ch * uhw] = s0[ch * (kGatherPix + 1)];
+            for (; ch < nch; ++ch, d0 += uhw) *d0 = st[ch * kGatherPix + (lane ^ (ch >> 2))];
         }
     }
 }
