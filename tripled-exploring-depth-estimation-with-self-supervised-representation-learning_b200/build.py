@@ -20,7 +20,7 @@ OUT = os.path.join(HERE, "libtdl.so")
 SOURCES = ["tdl_api.cu", "tdl_photo.cu", "tdl_smooth.cu", "tdl_feat.cu"]
 HEADERS = [os.path.join(CSRC, "tdl_common.cuh"), os.path.join(CSRC, "tdl_internal.h"), os.path.join(CSRC, "tdl_tma.cuh"),
            os.path.join(ROOT, "include", "tdl.h")]
-NVCC_FLAGS = (["-DTDL_DEBUG_OV"] if os.environ.get("TDL_DEBUG_OV") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
 

@@ -438,10 +438,14 @@ __global__ void __launch_bounds__(kNT, 2) photo_score_kernel(const PhotoDev p, c
                                                            const __grid_constant__ PhotoMaps wmaps) {
     constexpr int FW = kFW, FPLANE = kFPLANE, FGROUP = kFGROUP;
     extern __shared__ __align__(128) float smem_score[];
+    // S <= 2: the warped tiles are double-buffered (still two CTAs per SM) -- the TMA copies of scale s+1 fly while scale s
+    // is scored, and those of scale 0 travel with the target / source tiles, so the CTA waits for memory once, not 1 + nscales times
+    constexpr bool kDB = S <= 2;
     float* s_tgt = smem_score;                 // group 0: target
-    float* s_img = smem_score + FGROUP;        // groups 1..S: sources (identity terms), then warped per scale
+    float* s_img = smem_score + FGROUP;        // groups 1..S: sources (identity terms), then warped per scale (buffer A)
+    float* s_alt = s_img + S * FGROUP + 6 * kR * kNT;      // kDB: S more groups (buffer B), behind the statistics
     __shared__ float s_red[32];
-    __shared__ uint64_t s_bar;
+    __shared__ uint64_t s_bar, s_bar2;
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int b = blockIdx.z, tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
@@ -449,15 +453,22 @@ __global__ void __launch_bounds__(kNT, 2) photo_score_kernel(const PhotoDev p, c
     const size_t HW = (size_t)H * W;
     constexpr uint32_t kGroupBytes = 3 * FPLANE * sizeof(float);
 
-    if (tid == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
     if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_init(&s_bar2, 1);
         mbar_arrive_expect_tx(&s_bar, (1 + S) * kGroupBytes);
         tma_load_3d(s_tgt, &maps.tgt, &s_bar, tx0 - kFX0, ty0 - kFY0, b * 3);
 #pragma unroll
         for (int f = 0; f < S; ++f) tma_load_3d(s_img + f * FGROUP, &maps.img[f], &s_bar, tx0 - kFX0, ty0 - kFY0, b * 3);
+        if (kDB) {                             // warped tiles of scale 0 -> buffer B
+            mbar_arrive_expect_tx(&s_bar2, S * kGroupBytes);
+#pragma unroll
+            for (int f = 0; f < S; ++f)
+                tma_load_3d(s_alt + f * FGROUP, &wmaps.img[f], &s_bar2, tx0 - kFX0, ty0 - kFY0, b * 3);
+        }
     }
-    uint32_t parity = 0;
+    __syncthreads();                           // barrier initialisation visible to the waiting threads
+    uint32_t parity = 0, parity2 = 0;
     mbar_wait(&s_bar, parity);
     parity ^= 1;
     reflect_fix(smem_score, 1 + S, tx0, ty0, H, W, tid);
@@ -510,16 +521,40 @@ __global__ void __launch_bounds__(kNT, 2) photo_score_kernel(const PhotoDev p, c
 
     for (int s = 0; s < p.nscales; ++s) {
         // ---- stage the S warped tiles of this scale (written by photo_warp_kernel)
-        if (tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive_expect_tx(&s_bar, S * kGroupBytes);
+        float* s_cur = s_img;
+        if (kDB) {
+            // scale s was requested one step ago (scale 0: with the prologue); request scale s + 1 into the other buffer,
+            // which every thread has finished reading (the identity terms, or scale s - 1, ended with a CTA barrier)
+            const bool curB = (s & 1) == 0;
+            s_cur = curB ? s_alt : s_img;
+            if (tid == 0 && s + 1 < p.nscales) {
+                float* s_nxt = curB ? s_img : s_alt;
+                uint64_t* bar_nxt = curB ? &s_bar : &s_bar2;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive_expect_tx(bar_nxt, S * kGroupBytes);
 #pragma unroll
-            for (int f = 0; f < S; ++f)
-                tma_load_3d(s_img + f * FGROUP, &wmaps.img[s * S + f], &s_bar, tx0 - kFX0, ty0 - kFY0, b * 3);
+                for (int f = 0; f < S; ++f)
+                    tma_load_3d(s_nxt + f * FGROUP, &wmaps.img[(s + 1) * S + f], bar_nxt, tx0 - kFX0, ty0 - kFY0, b * 3);
+            }
+            if (curB) {
+                mbar_wait(&s_bar2, parity2);
+                parity2 ^= 1;
+            } else {
+                mbar_wait(&s_bar, parity);
+                parity ^= 1;
+            }
+        } else {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive_expect_tx(&s_bar, S * kGroupBytes);
+#pragma unroll
+                for (int f = 0; f < S; ++f)
+                    tma_load_3d(s_img + f * FGROUP, &wmaps.img[s * S + f], &s_bar, tx0 - kFX0, ty0 - kFY0, b * 3);
+            }
+            mbar_wait(&s_bar, parity);
+            parity ^= 1;
         }
-        mbar_wait(&s_bar, parity);
-        parity ^= 1;
-        reflect_fix(s_img, S, tx0, ty0, H, W, tid);
+        reflect_fix(s_cur, S, tx0, ty0, H, W, tid);
         __syncthreads();
 
         // ---- reprojection errors, automask, minimum over frames
@@ -553,7 +588,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_score_kernel(const PhotoDev p, c
 #pragma unroll
         for (int f = 0; f < S; ++f) {
             float rho[kR];
-            strip_reprojection<FW>(s_img + f * FGROUP, s_tgt, FPLANE, r0, c0, s_stats, rho);
+            strip_reprojection<FW>(s_cur + f * FGROUP, s_tgt, FPLANE, r0, c0, s_stats, rho);
 #pragma unroll
             for (int i = 0; i < kR; ++i) {
                 if (arg[i] < 0 || rho[i] < best[i]) {
@@ -653,6 +688,17 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     const int h = p.dh[s], w = p.dw[s];
     const float up = __ldg(p.dlosses + s) * p.photo_coef[s] / ((float)p.B * (float)H * (float)W);
 
+    // Everything the CTA needs from global memory is requested up front -- the TMA box copies, the arg-min bytes and
+    // the disparity taps below do not depend on shared memory -- so one memory latency sits on the critical path instead
+    // of three (cam/tables -> barrier -> gathers -> barrier -> tiles): 280 -> 2xx us on the bench shape.
+    if (kTMA && tid == 0) {
+        // one elected thread stages the target and the S warped tiles (halo 2) with 3-D TMA box copies
+        mbar_init(&s_bar, 1);
+        mbar_arrive_expect_tx(&s_bar, (uint32_t)((1 + S) * 3 * QPLANE * sizeof(float)));
+        tma_load_3d(s_tgt, &maps.tgt, &s_bar, tx0 - kQX0, ty0 - kQY0, b * 3);
+#pragma unroll
+        for (int f = 0; f < S; ++f) tma_load_3d(s_wrp + f * QGROUP, &maps.img[s * S + f], &s_bar, tx0 - kQX0, ty0 - kQY0, b * 3);
+    }
     if (tid < S * 12) {
         s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
         s_dP[tid] = 0.f;
@@ -662,16 +708,6 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     const float* s_iK = s_cam + TDL_MAX_SRC * 12;
     if (tid < kTW) up_index(tx0 + tid, p.sx[s], w, s_tx0[tid], s_tx1[tid], s_tlx[tid]);
     if (tid >= 32 && tid < 32 + kTH) up_index(ty0 + tid - 32, p.sy[s], h, s_ty0[tid - 32], s_ty1[tid - 32], s_tly[tid - 32]);
-    if (kTMA && tid == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (kTMA && tid == 0) {
-        // one elected thread stages the target and the S warped tiles (halo 2) with 3-D TMA box copies
-        mbar_arrive_expect_tx(&s_bar, (uint32_t)((1 + S) * 3 * QPLANE * sizeof(float)));
-        tma_load_3d(s_tgt, &maps.tgt, &s_bar, tx0 - kQX0, ty0 - kQY0, b * 3);
-#pragma unroll
-        for (int f = 0; f < S; ++f) tma_load_3d(s_wrp + f * QGROUP, &maps.img[s * S + f], &s_bar, tx0 - kQX0, ty0 - kQY0, b * 3);
-    }
-
     const DepthParams dp{p.min_disp, p.range};
     const float* db = p.disp[s] + (size_t)b * h * w;
     const unsigned char* am = p.argmin + ((size_t)s * p.B + b) * HW;
@@ -680,12 +716,27 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     // tiles, so it is computed here, while the TMA copies issued above are in flight
     const int r0 = wrp * kR;
     const int gx = tx0 + lane;
+    // the arg-min bytes of the tile (TMA path) are requested first so that they travel together with the disparity
+    // gathers below instead of after them (one global-memory latency less on the CTA's critical path)
+    constexpr int NITM = (QPLANE + kNT - 1) / kNT;
+    unsigned char mreg[NITM];
+    if (kTMA) {
+#pragma unroll
+        for (int it = 0; it < NITM; ++it) {
+            const int i = min(tid + it * kNT, QPLANE - 1);
+            const int r = i / QW, c = i - r * QW;
+            const int ry = ty0 - 2 + r, rx = tx0 - kQX0 + c;
+            const bool inside = ry >= 0 && ry < H && rx >= 0 && rx < W;
+            mreg[it] = inside ? am[(size_t)ry * W + rx] : (unsigned char)255;
+        }
+    }
+    float dval[kR];                       // up-sampled disparity of this thread's pixels (taps recomputed here, not read
+#pragma unroll                            // from the shared tables, so that the gathers start before the first barrier)
+    for (int i = 0; i < kR; ++i) dval[i] = up_value(db, w, up_tap(ty0 + r0 + i, gx, p.sy[s], p.sx[s], h, w));
+    __syncthreads();
     Geo geo[kR];
 #pragma unroll
-    for (int i = 0; i < kR; ++i) {
-        const UpTap ut{s_ty0[r0 + i], s_ty1[r0 + i], s_tx0[lane], s_tx1[lane], s_tly[r0 + i], s_tlx[lane]};
-        geo[i] = backproject(up_value(db, w, ut), dp, s_iK, gx, ty0 + r0 + i);
-    }
+    for (int i = 0; i < kR; ++i) geo[i] = backproject(dval[i], dp, s_iK, gx, ty0 + r0 + i);
 
     // ---- phase 1: target, argmin mask and the warped sources over the tile with halo 2.  When the forward
     //      materialised outputs[("color",f,s)] they are re-read (coalesced, bit-identical to what the forward
@@ -696,12 +747,9 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
         const bool have_warped = p.warped[s][0] != nullptr;
         constexpr int NIT = (QPLANE + kNT - 1) / kNT;
         if (kTMA) {
-            for (int i = tid; i < QPLANE; i += kNT) {
-                const int r = i / QW, c = i - r * QW;
-                const int ry = ty0 - 2 + r, rx = tx0 - kQX0 + c;
-                const bool inside = ry >= 0 && ry < H && rx >= 0 && rx < W;
-                s_mask[i] = inside ? am[(size_t)ry * W + rx] : (unsigned char)255;
-            }
+#pragma unroll
+            for (int it = 0; it < NITM; ++it)
+                if (tid + it * kNT < QPLANE) s_mask[tid + it * kNT] = mreg[it];
             mbar_wait(&s_bar, 0);
             // nn.ReflectionPad2d(1): the zero-filled cells one pixel outside the image take their mirror value
             const bool bl = tx0 == 0, br = tx0 + kTW >= W, bt_ = ty0 == 0, bb = ty0 + kTH >= H;
@@ -1014,7 +1062,7 @@ template <int S>
 static cudaError_t launch_score_t(const PhotoDev& p, cudaStream_t st) {
     PhotoMaps maps, wmaps;
     if (!encode_fwd_maps<S>(p, &maps, &wmaps)) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)(1 + S) * kFGROUP * sizeof(float) + (size_t)6 * kR * kNT * sizeof(float);
+    const size_t smem = (size_t)(1 + S + (S <= 2 ? S : 0)) * kFGROUP * sizeof(float) + (size_t)6 * kR * kNT * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(photo_score_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
