@@ -474,27 +474,31 @@ __global__ void __launch_bounds__(kNT, 2) photo_score_kernel(const PhotoDev p, c
     reflect_fix(smem_score, 1 + S, tx0, ty0, H, W, tid);
     __syncthreads();
 
-    // ---- area-downsampled target pyramid (F.interpolate(mode='area'), net.py:259) and disparity sums
-    for (int s = 0; s < p.nscales; ++s) {
-        const int fac = p.fac[s], cells = kTW / fac, h = p.dh[s], w = p.dw[s];
-        const int cj0 = ty0 / fac, ci0 = tx0 / fac;
-        const float inv = 1.f / (float)(fac * fac);
-        float dsum = 0.f;
-        for (int i = tid; i < cells * cells * 3; i += kNT) {
-            const int ch = i / (cells * cells), rem = i - ch * cells * cells;
-            const int cj = rem / cells, ci = rem - cj * cells;
-            if (cj0 + cj < h && ci0 + ci < w) {
-                const float* base = s_tgt + ch * FPLANE + (kFY0 + cj * fac) * FW + kFX0 + ci * fac;
-                float acc = 0.f;
-                for (int dy = 0; dy < fac; ++dy)
-                    for (int dx = 0; dx < fac; ++dx) acc += base[dy * FW + dx];
-                const size_t o = (((size_t)b * 3 + ch) * h + cj0 + cj) * w + ci0 + ci;
-                p.J[s][o] = acc * inv;
-                if (ch == 0) dsum += __ldg(p.disp[s] + ((size_t)b * h + cj0 + cj) * w + ci0 + ci);
+    // ---- area-downsampled target pyramid (F.interpolate(mode='area'), net.py:259) and disparity sums; the per-scale
+    //      sums stay in registers and are reduced over the CTA once, after the scale loop (no barriers in between)
+    float dsum[TDL_MAX_SCALES], lsum[TDL_MAX_SCALES];
+#pragma unroll
+    for (int s = 0; s < TDL_MAX_SCALES; ++s) dsum[s] = lsum[s] = 0.f;
+#pragma unroll
+    for (int s = 0; s < TDL_MAX_SCALES; ++s) {
+        if (s < p.nscales) {
+            const int fac = p.fac[s], cells = kTW / fac, h = p.dh[s], w = p.dw[s];
+            const int cj0 = ty0 / fac, ci0 = tx0 / fac;
+            const float inv = 1.f / (float)(fac * fac);
+            for (int i = tid; i < cells * cells * 3; i += kNT) {
+                const int ch = i / (cells * cells), rem = i - ch * cells * cells;
+                const int cj = rem / cells, ci = rem - cj * cells;
+                if (cj0 + cj < h && ci0 + ci < w) {
+                    const float* base = s_tgt + ch * FPLANE + (kFY0 + cj * fac) * FW + kFX0 + ci * fac;
+                    float acc = 0.f;
+                    for (int dy = 0; dy < fac; ++dy)
+                        for (int dx = 0; dx < fac; ++dx) acc += base[dy * FW + dx];
+                    const size_t o = (((size_t)b * 3 + ch) * h + cj0 + cj) * w + ci0 + ci;
+                    p.J[s][o] = acc * inv;
+                    if (ch == 0) dsum[s] += __ldg(p.disp[s] + ((size_t)b * h + cj0 + cj) * w + ci0 + ci);
+                }
             }
         }
-        dsum = block_sum(dsum, s_red);
-        if (tid == 0) atomicAdd(p.acc + ((size_t)s * p.B + b) * 4 + 1, (double)dsum);
     }
 
     // ---- per-thread strip: column `lane`, rows wrp*kR .. of the tile; window corner (r0, lane + kFX0 - 1)
@@ -598,20 +602,43 @@ __global__ void __launch_bounds__(kNT, 2) photo_score_kernel(const PhotoDev p, c
             }
             ++chan;
         }
-        float lsum = 0.f;
+        float ls = 0.f;
 #pragma unroll
         for (int i = 0; i < kR; ++i) {
             const int gy = ty0 + r0 + i;
             if (gx < W && gy < H) {
                 const size_t pix = (size_t)gy * W + gx;
-                lsum += best[i];
+                ls += best[i];
                 p.argmin[((size_t)s * p.B + b) * HW + pix] = (unsigned char)arg[i];
                 if (p.min_index[s]) p.min_index[s][(size_t)b * HW + pix] = arg[i];
             }
         }
-        lsum = block_sum(lsum, s_red);
-        if (tid == 0) atomicAdd(p.acc + ((size_t)s * p.B + b) * 4 + 0, (double)lsum);
-        __syncthreads();           // every thread is done with s_img before the next scale's TMA overwrites it
+#pragma unroll
+        for (int k = 0; k < TDL_MAX_SCALES; ++k)
+            if (k == s) lsum[k] = ls;
+        __syncthreads();           // every thread is done with this scale's tiles before a later TMA overwrites them
+    }
+    // ---- one CTA reduction for the 2 * nscales partial sums: warp shuffles, then warp 0 adds the kNT/32 warp totals
+    {
+        float* s_part = s_img;                 // [2 * TDL_MAX_SCALES][kNT / 32]; the tiles are no longer needed
+#pragma unroll
+        for (int k = 0; k < TDL_MAX_SCALES; ++k) {
+            const float a = warp_sum(lsum[k]), d = warp_sum(dsum[k]);
+            if (lane == 0) {
+                s_part[k * (kNT / 32) + wrp] = a;
+                s_part[(TDL_MAX_SCALES + k) * (kNT / 32) + wrp] = d;
+            }
+        }
+        __syncthreads();
+        if (tid < 2 * TDL_MAX_SCALES) {
+            const int k = tid % TDL_MAX_SCALES;
+            if (k < p.nscales) {
+                float t = 0.f;
+#pragma unroll
+                for (int j = 0; j < kNT / 32; ++j) t += s_part[tid * (kNT / 32) + j];
+                atomicAdd(p.acc + ((size_t)k * p.B + b) * 4 + (tid < TDL_MAX_SCALES ? 0 : 1), (double)t);
+            }
+        }
     }
 }
 
