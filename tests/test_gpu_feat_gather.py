@@ -78,6 +78,20 @@ def test_bucketed_gather_matches_atomic_scatter(B, C, h, w, S, shift):
             assert rel_l2(gb, ga) < 1e-5, (name, rel_l2(gb, ga))
 
 
+def test_batch_chunking_is_invisible(monkeypatch):
+    """The bucketed backward runs in batch chunks (G stays L2-resident); chunk sizes that do not divide the batch and a
+    chunk of one image must give the same gradients as the un-chunked run."""
+    args = _inputs(5, 8, 40, 64, 2, 4200, 0.05)
+    monkeypatch.delenv("TDL_FEAT_CHUNK", raising=False)
+    loss0, grads0 = _run(args, atomic=False)
+    for chunk in ("2", "1", "4"):
+        monkeypatch.setenv("TDL_FEAT_CHUNK", chunk)
+        loss1, grads1 = _run(args, atomic=False)
+        assert loss1 == loss0
+        for g0, g1 in zip(grads0, grads1):
+            assert rel_l2(g1, g0) < 1e-6, chunk
+
+
 def test_gather_path_without_scratch_falls_back(monkeypatch):
     """C % 4 != 0 cannot use the 16-byte G rows: the library must silently take the atomic kernel, same results."""
     args = _inputs(1, 6, 32, 48, 2, 4100, 0.0)

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
     const float* Pf = s_cam + max(fsel, 0) * 12;
     const Proj pr = project<true>(g, Pf, h, w, p.align_corners);
     const Bilin bt = bilin_taps(pr.ix, pr.iy, h, w);
-    const float up = active ? __ldg(p.dloss) * p.coef / ((float)p.B * (float)h * (float)w) / (float)C : 0.f;
+    const float up = active ? __ldg(p.dloss) * p.coef / ((float)p.Bnorm * (float)h * (float)w) / (float)C : 0.f;
     const float* sb = p.src[0];
     float* dsb = kGradFeat ? p.d_src[0] : nullptr;
 #pragma unroll
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(kBucketRows * 32) feat_bwd_bucket_kernel(const
     const float* Pf = s_cam + max(fsel, 0) * 12;
     const Proj pr = project<true>(g, Pf, h, w, p.align_corners);
     const Bilin bt = bilin_taps(pr.ix, pr.iy, h, w);
-    const float up = active ? __ldg(p.dloss) * p.coef / ((float)p.B * (float)h * (float)w) / (float)C : 0.f;
+    const float up = active ? __ldg(p.dloss) * p.coef / ((float)p.Bnorm * (float)h * (float)w) / (float)C : 0.f;
     const float* sb = p.src[0];
 #pragma unroll
     for (int f = 1; f < TDL_MAX_SRC; ++f)
@@ -362,8 +362,10 @@ __global__ void __launch_bounds__(kBucketRows * 32) feat_bwd_bucket_kernel(const
                 if (slot < kFeatBucketCap) {
                     ent[(size_t)o * kFeatBucketCap + slot] = make_int2(pix, __float_as_int(wgt));
                 } else {
-const int k = atomicAdd(p.ov_cnt, 1);      // (warp-aggregating this counter measured 38 us SLOWER)
-                    p.ov_ent[k] = make_int4(fb, o, pix, __float_as_int(wgt));
+                    // per-image counter and list: one global counter serialised ~270 k same-address atomics at batch 64
+                    // (warp-aggregating the counter instead measured 38 us SLOWER at batch 8)
+                    const int k = atomicAdd(p.ov_cnt + b, 1);
+                    p.ov_ent[(size_t)b * 4 * hw + k] = make_int4(fsel, o, pix, __float_as_int(wgt));
                 }
             }
         };
@@ -568,17 +570,18 @@ __global__ void __launch_bounds__(kGatherWarps * 32) feat_gather_kernel(const Fe
 }
 
 __global__ void __launch_bounds__(256) feat_overflow_kernel(const FeatDev p) {
-    const int n = *p.ov_cnt;
+    const int b = blockIdx.y;
+    const int n = p.ov_cnt[b];
     const int ngrp = (int)(gridDim.x * blockDim.x) >> 4;
     const int l16 = threadIdx.x & 15;
     const int hw = p.h * p.w, C = p.C;
+    const int4* list = p.ov_ent + (size_t)b * 4 * hw;
     for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) >> 4; i < n; i += ngrp) {
-        const int4 e = p.ov_ent[i];
-        const int f = e.x / p.B, b = e.x - f * p.B;
+        const int4 e = list[i];                              // (frame, source pixel, target pixel, weight)
         float* dst = p.d_src[0];
 #pragma unroll
         for (int k = 1; k < TDL_MAX_SRC; ++k)
-            if (k == f) dst = p.d_src[k];
+            if (k == e.x) dst = p.d_src[k];
         dst += (size_t)b * C * hw + e.y;
         const float wgt = __int_as_float(e.w);
         const float* Gr = p.G + ((size_t)b * hw + e.z) * C;
@@ -628,7 +631,7 @@ cudaError_t launch_feat_bwd_gather(const FeatDev& p, cudaStream_t st) {
 }
 
 cudaError_t launch_feat_bwd_overflow(const FeatDev& p, cudaStream_t st) {
-    feat_overflow_kernel<<<148 * 8, 256, 0, st>>>(p);
+    feat_overflow_kernel<<<dim3((148 * 8 + p.B - 1) / p.B, p.B), 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -67,6 +67,7 @@ struct SmoothDev {
 // ---- feature-metric ----------------------------------------------------------------
 struct FeatDev {
     int B, C, h, w, S;
+    int Bnorm;                   // batch size of the mean (== B except for the batch chunks of the bucketed backward)
     int dh, dw;
     float sy, sx;
     int align_corners;
@@ -91,8 +92,8 @@ struct FeatDev {
     float* G;                    // [B][h*w][C]  d loss / d warped value, channel-last
     int* bk_cnt;                 // [S][B][h*w]  taps registered per source pixel
     int2* bk_ent;                // [S][B][h*w][kFeatBucketCap]  (target pixel, weight bits)
-    int* ov_cnt;                 // [1]          length of the overflow list
-    int4* ov_ent;                // [4*B*h*w]    (frame*B + b, source pixel, target pixel, weight bits)
+    int* ov_cnt;                 // [B]          length of each image's overflow list
+    int4* ov_ent;                // [B][4*h*w]   (frame, source pixel, target pixel, weight bits)
 };
 constexpr int kFeatBucketCap = 8;
 
