@@ -90,6 +90,13 @@ int check_photo(const tdl_photo_args* a, bool bwd, PhotoDev* d) {
     d->automask = a->automask != 0;
     d->use_tma = getenv("TDL_NO_TMA") == nullptr;
     d->split_fwd = getenv("TDL_FUSED_FWD") == nullptr;
+    {
+        // tiles with <= 128 selected windows (of 1156 incl. halo, all frames) take the scatter path; 128 is also the hard
+        // limit (9 live pixels per window must fit the tile's list).  Tests: 0 forces the dense backward everywhere.
+        const char* e = getenv("TDL_PHOTO_SPARSE_MAX");
+        const int v = e ? atoi(e) : 128;
+        d->sparse_max = v < 0 ? 0 : (v > 128 ? 128 : v);
+    }
     d->align_corners = a->align_corners != 0;
     d->min_disp = (float)(1.0 / a->max_depth);
     d->range = (float)(1.0 / a->min_depth - 1.0 / a->max_depth);

@@ -20,6 +20,8 @@ struct PhotoDev {
     int automask, align_corners;
     int use_tma;                 // stage image tiles with TMA box copies when the tensors allow it
     int split_fwd;               // forward = warp kernel + TMA-staged scoring kernel (needs materialised warps)
+    int sparse_max;              // backward: tiles with at most this many selected windows (of 1156 incl. halo) scatter
+                                 // their adjoint instead of running the dense box-sum gather (auto-masked regions)
     float min_disp, range;
     uint64_t seed;
     const float* target;

@@ -703,6 +703,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
     __shared__ float s_dP[TDL_MAX_SRC * 12];
     __shared__ int s_cnt[TDL_MAX_SRC];
+    __shared__ int s_nall;              // selected windows of the tile (all frames); later the live-pair counter
     __shared__ unsigned short s_list[PH * PW];
     __shared__ int s_tx0[kTW], s_tx1[kTW], s_ty0[kTH], s_ty1[kTH];
     __shared__ float s_tlx[kTW], s_tly[kTH];
@@ -731,6 +732,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
         s_dP[tid] = 0.f;
     }
     if (tid >= 128 && tid < 128 + TDL_MAX_SRC) s_cnt[tid - 128] = 0;
+    if (tid == 255) s_nall = 0;
     if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
     const float* s_iK = s_cam + TDL_MAX_SRC * 12;
     if (tid < kTW) up_index(tx0 + tid, p.sx[s], w, s_tx0[tid], s_tx1[tid], s_tlx[tid]);
@@ -761,9 +763,6 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
 #pragma unroll                            // from the shared tables, so that the gathers start before the first barrier)
     for (int i = 0; i < kR; ++i) dval[i] = up_value(db, w, up_tap(ty0 + r0 + i, gx, p.sy[s], p.sx[s], h, w));
     __syncthreads();
-    Geo geo[kR];
-#pragma unroll
-    for (int i = 0; i < kR; ++i) geo[i] = backproject(dval[i], dp, s_iK, gx, ty0 + r0 + i);
 
     // ---- phase 1: target, argmin mask and the warped sources over the tile with halo 2.  When the forward
     //      materialised outputs[("color",f,s)] they are re-read (coalesced, bit-identical to what the forward
@@ -861,26 +860,156 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     for (int i = 0; i < kR; ++i) gd[i] = 0.f;
     const float g_ssim = up * 0.85f / 3.f, g_l1 = up * 0.15f / 3.f;
 
+    // ---- phase 2a: the windows (tile + halo 1) whose arg-min is a WARPED frame carry gradient; they are compacted into
+    //      one list (window cell | frame << 11) so that the heavy statistics run with full warps.
+    const int chan0 = p.automask ? S : 0;
+    for (int i = tid; i < PH * PW; i += kNT) {
+        const int r = i / PW, c = i - r * PW;
+        const int q = (r + 1) * QW + c + kQX0 - 1;
+        const int f = (int)s_mask[q] - chan0;
+        if (f >= 0 && f < S) {
+            atomicAdd(&s_cnt[f], 1);
+            s_list[atomicAdd(&s_nall, 1)] = (unsigned short)(q | (f << 11));
+        }
+    }
+    __syncthreads();
+    const int n_all = s_nall;
+    if (n_all == 0) return;                       // automasking: nothing selected in this tile (CTA-uniform)
+
+    if (n_all <= p.sparse_max) {
+        // ---- sparse tile (auto-masked / static regions: a few selected windows).  The dense path below would spend its
+        //      time on box sums of zeros and on strips with one live pixel; here the selected windows SCATTER their adjoint
+        //      into per-frame tile accumulators, the (frame, pixel) pairs that received something are compacted, and one
+        //      thread per live pair runs the sampling / projection chain.  Same arithmetic, different summation order.
+        constexpr int TP = kTH * kTW;
+        float* s_G = s_coef;                                  // [S][3][TP]
+        for (int i = tid; i < S * 3 * TP; i += kNT) s_G[i] = 0.f;
+        __syncthreads();
+        for (int e = tid; e < 3 * n_all; e += kNT) {          // one thread per (selected window, channel)
+            const int ent = s_list[e / 3], ch = e - (e / 3) * 3;
+            const int q = ent & 2047, f = ent >> 11;
+            const int r = q / QW, c = q - r * QW;
+            const int wy = ty0 - kQY0 + r, wx = tx0 - kQX0 + c;           // image coordinates of the window centre
+            const float* xs = s_wrp + f * QGROUP + ch * QPLANE + q;
+            const float* ys = s_tgt + ch * QPLANE + q;
+            float* Gf = s_G + (f * 3 + ch) * TP;
+            float cA, cB, cC;
+            window_adjoint<QW>(xs, ys, g_ssim * (1.f / 9.f), cA, cB, cC);
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    // nn.ReflectionPad2d(1): a tap outside the image IS its mirror pixel (the staged cell holds the
+                    // mirror value), which gives the border multiplicities of the dense path for free
+                    const int ly = reflect1(wy + dy, H) - ty0, lx = reflect1(wx + dx, W) - tx0;
+                    if (ly >= 0 && ly < kTH && lx >= 0 && lx < kTW)
+                        atomicAdd(&Gf[ly * kTW + lx], cA + 2.f * xs[dy * QW + dx] * cB + ys[dy * QW + dx] * cC);
+                }
+            }
+            const int ly = wy - ty0, lx = wx - tx0;
+            if (ly >= 0 && ly < kTH && lx >= 0 && lx < kTW) {                 // robust-L1 term of the centre pixel
+                const float df = xs[0] - ys[0];
+                atomicAdd(&Gf[ly * kTW + lx], g_l1 * df * rsqrt_approx(df * df + kL1Eps2));
+            }
+        }
+        if (tid == 0) s_nall = 0;                             // reused as the live-pair counter (everyone has read n_all)
+        __syncthreads();
+        for (int i = tid; i < S * TP; i += kNT) {             // live (frame, pixel) pairs; <= 9 * n_all <= PH * PW entries
+            const int f = i / TP, px = i - f * TP;
+            const int ly = px / kTW, lx = px - ly * kTW;
+            const float* Gf = s_G + f * 3 * TP + px;
+            if (tx0 + lx < W && ty0 + ly < H && (Gf[0] != 0.f || Gf[TP] != 0.f || Gf[2 * TP] != 0.f))
+                s_list[atomicAdd(&s_nall, 1)] = (unsigned short)(px | (f << 11));
+        }
+        __syncthreads();
+        const int n_act = s_nall;
+        float* dd = p.d_disp[s] + (size_t)b * h * w;
+        for (int e0 = wrp * 32; e0 < n_act; e0 += kNT) {      // warp-uniform trip count: the dP reduction below is warp-wide
+            const int e = e0 + lane;
+            const bool on = e < n_act;
+            const int ent = on ? s_list[e] : 0, i = ent & 2047, f = ent >> 11;
+            const int ly = i / kTW, lx = i - ly * kTW;
+            const int py = ty0 + ly, px = tx0 + lx;
+            const float* Pf = s_cam + f * 12;
+            const float* sbase = p.src[0];
+#pragma unroll
+            for (int k = 1; k < S; ++k)
+                if (k == f) sbase = p.src[k];
+            sbase += (size_t)b * 3 * HW;
+            const UpTap ut = up_tap(py, px, p.sy[s], p.sx[s], h, w);
+            const Geo g = backproject(up_value(db, w, ut), dp, s_iK, px, py);
+            const Proj pr = project<true>(g, Pf, H, W, p.align_corners);
+            const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
+            const float* q = sbase + (size_t)bt.y0 * W + bt.x0;
+            const int dx = bt.vx ? 1 : 0, dy = bt.vy ? W : 0;
+            float gix = 0.f, giy = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float v00 = __ldg(q + ch * HW), v01 = bt.vx ? __ldg(q + ch * HW + dx) : 0.f;
+                const float v10 = bt.vy ? __ldg(q + ch * HW + dy) : 0.f;
+                const float v11 = (bt.vx && bt.vy) ? __ldg(q + ch * HW + dy + dx) : 0.f;
+                const float dix = -v00 * bt.ey + v01 * bt.ey - v10 * bt.ay + v11 * bt.ay;
+                const float diy = -v00 * bt.ex - v01 * bt.ax + v10 * bt.ex + v11 * bt.ax;
+                const float Gc = on ? s_G[(f * 3 + ch) * TP + i] : 0.f;
+                gix += Gc * dix;
+                giy += Gc * diy;
+            }
+            const float gu = gix * pr.mx, gv = giy * pr.my;
+            const float rz = __frcp_rn(pr.z);
+            const float gp0 = gu * rz, gp1 = gv * rz, gp2 = -(gu * pr.u + gv * pr.v) * rz;
+            float aP[12];
+            aP[0] = gp0 * g.X0; aP[1] = gp0 * g.X1; aP[2] = gp0 * g.X2; aP[3] = gp0;
+            aP[4] = gp1 * g.X0; aP[5] = gp1 * g.X1; aP[6] = gp1 * g.X2; aP[7] = gp1;
+            aP[8] = gp2 * g.X0; aP[9] = gp2 * g.X1; aP[10] = gp2 * g.X2; aP[11] = gp2;
+#pragma unroll 1
+            for (int ff = 0; ff < S; ++ff) {                  // 12-value warp reduction per frame, one shared atomic per value
+                float a2[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) a2[k] = (on && f == ff) ? aP[k] : 0.f;
+                float tot;
+                const int slot = warp_sum12(a2, tot);
+                if (slot >= 0 && tot != 0.f) atomicAdd(&s_dP[ff * 12 + slot], tot);
+            }
+            if (on && (gp0 != 0.f || gp1 != 0.f || gp2 != 0.f)) {
+                const float gX0 = Pf[0] * gp0 + Pf[4] * gp1 + Pf[8] * gp2;
+                const float gX1 = Pf[1] * gp0 + Pf[5] * gp1 + Pf[9] * gp2;
+                const float gX2 = Pf[2] * gp0 + Pf[6] * gp1 + Pf[10] * gp2;
+                const float gD = gX0 * g.r0 + gX1 * g.r1 + gX2 * g.r2;
+                const float gdisp = -p.range * g.D * g.D * gD;
+                const float hy = 1.f - ut.ly, hx = 1.f - ut.lx;   // adjoint of the bilinear up-sampling, straight to d_disp_s
+                atomicAdd(dd + (size_t)ut.y0 * w + ut.x0, hy * hx * gdisp);
+                atomicAdd(dd + (size_t)ut.y0 * w + ut.x1, hy * ut.lx * gdisp);
+                atomicAdd(dd + (size_t)ut.y1 * w + ut.x0, ut.ly * hx * gdisp);
+                atomicAdd(dd + (size_t)ut.y1 * w + ut.x1, ut.ly * ut.lx * gdisp);
+            }
+        }
+        __syncthreads();
+        if (tid < S * 12 && s_dP[tid] != 0.f) atomicAdd(p.dP + ((size_t)b * S) * 12 + tid, s_dP[tid]);
+        return;
+    }
+
+    // ---- dense tile: depth / ray / camera point of this thread's strip, then per frame the coefficient planes
+    Geo geo[kR];
+#pragma unroll
+    for (int i = 0; i < kR; ++i) geo[i] = backproject(dval[i], dp, s_iK, gx, ty0 + r0 + i);
+
 #pragma unroll 1
     for (int f = 0; f < S; ++f) {
-        const int chan = (p.automask ? S : 0) + f;
-        // ---- phase 2: SSIM adjoint coefficients of every window centre (tile + halo 1).  Only windows whose
-        //      arg-min is this source frame carry gradient: they are compacted into a list first so that the
-        //      heavy statistics run with full warps and an even share per thread; the others just store zeros.
+        const int chan = chan0 + f;
+        if (s_cnt[f] == 0) continue;              // CTA-uniform
+        // ---- phase 2b: SSIM adjoint coefficients of every window centre; the unselected windows store zeros
         for (int i = tid; i < PH * PW; i += kNT) {
             const int r = i / PW, c = i - r * PW;
             const int q = (r + 1) * QW + c + kQX0 - 1;
-            if (s_mask[q] == chan) {
-                s_list[atomicAdd(&s_cnt[f], 1)] = (unsigned short)q;
-            } else {
+            if (s_mask[q] != chan) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) s_coef[k * QPLANE + q] = 0.f;
             }
         }
-        __syncthreads();
-        const int n_sel = s_cnt[f];
-        for (int e = tid; e < n_sel; e += kNT) {
-            const int q = s_list[e];
+        for (int e = tid; e < n_all; e += kNT) {
+            const int ent = s_list[e];
+            if ((ent >> 11) != f) continue;
+            const int q = ent & 2047;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 float cA, cB, cC;
@@ -1016,9 +1145,9 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     // ---- phase 4: adjoint of the bilinear up-sampling of disp_s, folded inside the tile
     float* s_g = s_coef;                        // [kTH][kTW]
     float* s_t = s_coef + kTH * kTW;            // [kTH][kTW + 2]
+    if (tid < S * 12 && s_dP[tid] != 0.f) atomicAdd(p.dP + ((size_t)b * S) * 12 + tid, s_dP[tid]);
 #pragma unroll
     for (int i = 0; i < kR; ++i) s_g[(r0 + i) * kTW + lane] = gd[i];
-    if (tid < S * 12) atomicAdd(p.dP + ((size_t)b * S) * 12 + tid, s_dP[tid]);
     __syncthreads();
     const int ilo = s_tx0[0], ihi = s_tx1[kTW - 1], ni = ihi - ilo + 1;       // <= kTW + 1
     const int jlo = s_ty0[0], jhi = s_ty1[kTH - 1], nj = jhi - jlo + 1;
