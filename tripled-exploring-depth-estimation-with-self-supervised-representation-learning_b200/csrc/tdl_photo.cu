@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     __shared__ float s_dP[TDL_MAX_SRC * 12];
     __shared__ int s_cnt[TDL_MAX_SRC];
     __shared__ int s_nall;              // selected windows of the tile (all frames); later the live-pair counter
-    __shared__ unsigned short s_list[PH * PW];
+    __shared__ unsigned short s_list[PH * PW + 128];   // selected windows (<= PH*PW); sparse path: 128 windows + 9*128 live pairs
     __shared__ int s_tx0[kTW], s_tx1[kTW], s_ty0[kTH], s_ty1[kTH];
     __shared__ float s_tlx[kTW], s_tly[kTH];
 
@@ -883,8 +883,12 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
         //      thread per live pair runs the sampling / projection chain.  Same arithmetic, different summation order.
         constexpr int TP = kTH * kTW;
         float* s_G = s_coef;                                  // [S][3][TP]
+        unsigned* s_bits = reinterpret_cast<unsigned*>(s_coef + S * 3 * TP);   // [S][TP / 32]: pixel already in the live list
         for (int i = tid; i < S * 3 * TP; i += kNT) s_G[i] = 0.f;
-        __syncthreads();
+        if (tid < S * TP / 32) s_bits[tid] = 0u;
+        __syncthreads();                                      // (everyone has read n_all: the counter can be reused)
+        if (tid == 0) s_nall = 0;
+        unsigned short* s_live = s_list + 128;                // <= 9 * n_all <= 1152 entries, behind the <= 128 windows
         for (int e = tid; e < 3 * n_all; e += kNT) {          // one thread per (selected window, channel)
             const int ent = s_list[e / 3], ch = e - (e / 3) * 3;
             const int q = ent & 2047, f = ent >> 11;
@@ -902,8 +906,14 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
                     // nn.ReflectionPad2d(1): a tap outside the image IS its mirror pixel (the staged cell holds the
                     // mirror value), which gives the border multiplicities of the dense path for free
                     const int ly = reflect1(wy + dy, H) - ty0, lx = reflect1(wx + dx, W) - tx0;
-                    if (ly >= 0 && ly < kTH && lx >= 0 && lx < kTW)
-                        atomicAdd(&Gf[ly * kTW + lx], cA + 2.f * xs[dy * QW + dx] * cB + ys[dy * QW + dx] * cC);
+                    if (ly >= 0 && ly < kTH && lx >= 0 && lx < kTW) {
+                        const int px = ly * kTW + lx;
+                        atomicAdd(&Gf[px], cA + 2.f * xs[dy * QW + dx] * cB + ys[dy * QW + dx] * cC);
+                        // the channel-0 thread of the window enters the pixel into the live list, once per (frame, pixel)
+                        if (ch == 0 && tx0 + lx < W && ty0 + ly < H &&
+                            !(atomicOr(&s_bits[f * (TP / 32) + (px >> 5)], 1u << (px & 31)) & (1u << (px & 31))))
+                            s_live[atomicAdd(&s_nall, 1)] = (unsigned short)(px | (f << 11));
+                    }
                 }
             }
             const int ly = wy - ty0, lx = wx - tx0;
@@ -912,22 +922,13 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
                 atomicAdd(&Gf[ly * kTW + lx], g_l1 * df * rsqrt_approx(df * df + kL1Eps2));
             }
         }
-        if (tid == 0) s_nall = 0;                             // reused as the live-pair counter (everyone has read n_all)
-        __syncthreads();
-        for (int i = tid; i < S * TP; i += kNT) {             // live (frame, pixel) pairs; <= 9 * n_all <= PH * PW entries
-            const int f = i / TP, px = i - f * TP;
-            const int ly = px / kTW, lx = px - ly * kTW;
-            const float* Gf = s_G + f * 3 * TP + px;
-            if (tx0 + lx < W && ty0 + ly < H && (Gf[0] != 0.f || Gf[TP] != 0.f || Gf[2 * TP] != 0.f))
-                s_list[atomicAdd(&s_nall, 1)] = (unsigned short)(px | (f << 11));
-        }
         __syncthreads();
         const int n_act = s_nall;
         float* dd = p.d_disp[s] + (size_t)b * h * w;
         for (int e0 = wrp * 32; e0 < n_act; e0 += kNT) {      // warp-uniform trip count: the dP reduction below is warp-wide
             const int e = e0 + lane;
             const bool on = e < n_act;
-            const int ent = on ? s_list[e] : 0, i = ent & 2047, f = ent >> 11;
+            const int ent = on ? s_live[e] : 0, i = ent & 2047, f = ent >> 11;
             const int ly = i / kTW, lx = i - ly * kTW;
             const int py = ty0 + ly, px = tx0 + lx;
             const float* Pf = s_cam + f * 12;
