@@ -320,7 +320,10 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
 // transpose with full 128-byte lines -- no memset of d_src, no float atomics.  Buckets hold kFeatBucketCap taps; the rare
 // excess goes to an overflow list that feat_overflow_kernel adds with atomics afterwards.
 constexpr int kBucketRows = 4;     // CTA = 32 columns x 4 rows, one warp per row (8 rows: same time, 16 rows: 25 % slower)
-__global__ void __launch_bounds__(kBucketRows * 32) feat_bwd_bucket_kernel(const FeatDev p) {
+// min-blocks = 1 on purpose: with the bare thread bound ptxas settles for 72 registers and a shallow load schedule (143 us);
+// told that one resident CTA is acceptable it uses 125 registers, keeps a whole channel batch of gathers in flight and the
+// kernel takes 134 us at 4 CTAs/SM (measured)
+__global__ void __launch_bounds__(kBucketRows * 32, 1) feat_bwd_bucket_kernel(const FeatDev p) {
     __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
     __shared__ float s_dP[TDL_MAX_SRC * 12];
     const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5;
