@@ -47,3 +47,14 @@ def test_each_backward_strategy_matches_oracle(monkeypatch, setting):
     monkeypatch.setenv("TDL_PHOTO_SPARSE_MAX", setting)
     rec = _synthetic_record("baseline", 1, 64, 96, 0, 5100, frames="waves")
     _check(rec, f"baseline-sparse_max={setting}")
+
+
+@pytest.mark.parametrize("env", [{"TDL_NO_TMA": "1"}, {"TDL_FUSED_FWD": "1"}, {"TDL_NO_TMA": "1", "TDL_PHOTO_SPARSE_MAX": "0"}])
+def test_fallback_kernels_match_oracle(monkeypatch, env):
+    """The plain-load variants (no TMA: what a tensor that TMA cannot describe gets -- unaligned base, odd strides) and the fused forward kernel (what
+    non-materialised warps get) are product code too: same oracle comparison as the default path."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rec = _synthetic_record("baseline", 1, 64, 96, 0, 5200, frames="waves")
+    _check(rec, f"baseline-{env}")
+
