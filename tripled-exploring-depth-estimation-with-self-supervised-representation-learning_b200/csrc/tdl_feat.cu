@@ -3,11 +3,14 @@
 //   generate_features_pred + compute_perceptional_loss + min over source frames
 //   mono/model/mono_fm/net.py:59-61,111-118,172-199; mono/model/mono_fm_joint_inpaint/net.py:58-70
 //
-// One thread = one feature-map pixel.  The warp of a pixel is computed once per source
-// frame (same projection code as the photometric path, half-resolution intrinsics), then
-// the C channels are streamed: lanes hold consecutive x, so the target reads and the
-// warped-feature writes are fully coalesced and the 4-tap gathers hit neighbouring lines.
-// HBM-bound: (1 + S) * C * 4 B read + S * C * 4 B written per pixel in the forward.
+// Forward / per-pixel backward: one thread = one feature-map pixel.  The warp of a pixel is computed once per source
+// frame (same projection code as the photometric path, half-resolution intrinsics), then the C channels are streamed:
+// lanes hold consecutive x, so the target reads and the warped-feature writes are fully coalesced; the 4-tap gathers
+// hit neighbouring lines for a smooth flow and one line per lane for the bench's pixel-level flow, which makes these
+// kernels L1/TEX-wavefront bound there (ncu: 85 % forward, 55 % backward).
+// Algorithmic traffic: (1 + S) * C * 4 B read + S * C * 4 B written per pixel in the forward.
+// Backward with trainable features: grid_sample's d_src scatter runs as a bucketed GATHER (feat_bwd_bucket_kernel +
+// feat_gather_kernel + feat_overflow_kernel below); feat_bwd_kernel<true> is the atomic-scatter fallback.
 #include "tdl_common.cuh"
 #include "tdl_internal.h"
 
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(kFeatNT) feat_bwd_kernel(const FeatDev p) {
 //   * registers its (up to) four taps in the bucket of the source pixel they touch: (target pixel, weight), one integer
 //     atomic per tap instead of one float reduction per tap AND channel;
 // then feat_gather_kernel walks the source pixels: 16 lanes x float4 = 64 channels read the G rows of the registered taps
-// (256 contiguous bytes each), accumulate in registers, and the CTA writes the NCHW d_src tile through a shared-memory
+// (256 contiguous bytes each), accumulate in registers, and each warp writes its NCHW d_src tile through a shared-memory
 // transpose with full 128-byte lines -- no memset of d_src, no float atomics.  Buckets hold kFeatBucketCap taps; the rare
 // excess goes to an overflow list that feat_overflow_kernel adds with atomics afterwards.
 constexpr int kBucketRows = 4;     // CTA = 32 columns x 4 rows, one warp per row (8 rows: same time, 16 rows: 25 % slower)
