@@ -254,11 +254,11 @@ int tdl_photo_fwd(const tdl_photo_args* a, tdl_stream_t stream) {
     const int rc = check_photo(a, false, &d);
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDL_KERNEL("memset", cudaMemsetAsync(d.acc, 0, (size_t)a->nscales * a->B * 4 * sizeof(double), st));
-    if (photo_fwd_can_split(d)) {
+    if (photo_fwd_can_split(d)) {                             // (photo_warp clears the accumulators itself)
         TDL_KERNEL("photo_warp", launch_photo_warp(d, st));
         TDL_KERNEL("photo_score", launch_photo_score(d, st));
     } else {
+        TDL_KERNEL("memset", cudaMemsetAsync(d.acc, 0, (size_t)a->nscales * a->B * 4 * sizeof(double), st));
         TDL_KERNEL("photo_fwd", launch_photo_fwd(d, st));
     }
     SmoothDev sm;
@@ -273,9 +273,10 @@ int tdl_photo_bwd(const tdl_photo_args* a, tdl_stream_t stream) {
     const int rc = check_photo(a, true, &d);
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TDL_KERNEL("memset", cudaMemsetAsync(a->dP, 0, (size_t)a->B * a->S * 12 * sizeof(float), st));
     SmoothDev sm;
     photo_smooth_levels(a, d, true, &sm);
+    sm.zero_ptr = a->dP;                                      // dP (accumulated by photo_bwd) is cleared by smooth_bwd's first CTA
+    sm.zero_n = a->B * a->S * 12;
     TDL_KERNEL("smooth_bwd", launch_smooth_bwd(sm, st));       // writes d_disp[s] (=), the photometric kernel adds to it
     TDL_KERNEL("photo_bwd", launch_photo_bwd(d, st));
     return TDL_OK;
@@ -309,7 +310,7 @@ static FeatScratchLayout feat_scratch_layout(int Bfull, int C, int h, int w, int
     const int B = feat_chunk_images(Bfull, C, h, w);
     const uint64_t hw = (uint64_t)h * w;
     L.cnt_off = 0;
-    L.hdr_bytes = align_up((uint64_t)B * sizeof(int), 256);                  // ov_cnt[B]
+    L.hdr_bytes = align_up((uint64_t)B * sizeof(int), 256) + align_up((uint64_t)B * S * 12 * sizeof(float), 256);   // ov_cnt[B] | dP_acc[B][S][12]
     L.cnt_bytes = L.hdr_bytes + align_up((uint64_t)S * B * hw * sizeof(int), 256);
     L.ent_off = L.cnt_off + L.cnt_bytes;
     L.ov_off = L.ent_off + align_up((uint64_t)S * B * hw * kFeatBucketCap * sizeof(int2), 256);
@@ -362,6 +363,7 @@ static int check_feat(const tdl_feat_args* a, bool bwd, FeatDev* d) {
             (reinterpret_cast<uintptr_t>(a->bwd_scratch) & 15) == 0 && getenv("TDL_FEAT_ATOMIC") == nullptr) {
             char* sc = static_cast<char*>(a->bwd_scratch);
             d->ov_cnt = reinterpret_cast<int*>(sc + L.cnt_off);
+            d->dP_acc = reinterpret_cast<float*>(sc + L.cnt_off + align_up((uint64_t)feat_chunk_images(a->B, a->C, a->h, a->w) * sizeof(int), 256));
             d->bk_cnt = reinterpret_cast<int*>(sc + L.cnt_off + L.hdr_bytes);
             d->bk_ent = reinterpret_cast<int2*>(sc + L.ent_off);
             d->ov_ent = reinterpret_cast<int4*>(sc + L.ov_off);
@@ -388,7 +390,8 @@ int tdl_feat_bwd(const tdl_feat_args* a, tdl_stream_t stream) {
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t fbytes = (size_t)a->B * a->C * a->h * a->w * sizeof(float);
-    TDL_KERNEL("memset", cudaMemsetAsync(a->dP, 0, (size_t)a->B * a->S * 12 * sizeof(float), st));
+    if (!d.G)        // (bucketed path: dP is accumulated in the zeroed scratch header and written by the gather kernel)
+        TDL_KERNEL("memset", cudaMemsetAsync(a->dP, 0, (size_t)a->B * a->S * 12 * sizeof(float), st));
     if (a->disp_h != a->h || a->disp_w != a->w)
         TDL_KERNEL("memset", cudaMemsetAsync(a->d_disp, 0, (size_t)a->B * a->disp_h * a->disp_w * sizeof(float), st));
     if (d.G) {       // bucketed gather: per-pixel kernel registers taps + writes G, gather kernel writes d_src (no memset)

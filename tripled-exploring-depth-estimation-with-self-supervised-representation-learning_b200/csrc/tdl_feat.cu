@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(kBucketRows * 32, 1) feat_bwd_bucket_kernel(co
         }
     }
     __syncthreads();
-    if (tid < S * 12 && s_dP[tid] != 0.f) atomicAdd(p.dP + (size_t)b * S * 12 + tid, s_dP[tid]);
+    if (tid < S * 12 && s_dP[tid] != 0.f) atomicAdd(p.dP_acc + (size_t)b * S * 12 + tid, s_dP[tid]);
 }
 
 constexpr int kGatherWarps = 4;     // warps per CTA; every warp owns one tile and never synchronises with the others
@@ -478,6 +478,8 @@ __global__ void __launch_bounds__(kGatherWarps * 32) feat_gather_kernel(const Fe
     const int fb = blockIdx.y;                               // frame * B + b
     const int f = fb / p.B, b = fb - f * p.B;
     const int hw = p.h * p.w, C = p.C;
+    if (blockIdx.x == 0 && blockIdx.y == 0)                  // dP of the per-pixel kernel: scratch accumulator -> output
+        for (int i = threadIdx.x; i < p.B * p.S * 12; i += kGatherWarps * 32) p.dP[i] = p.dP_acc[i];
     const int o0 = (blockIdx.x * kGatherWarps + wq) * kGatherPix;
     if (o0 >= hw) return;
     float* dst = p.d_src[0];

@@ -63,6 +63,8 @@ struct SmoothLevel {
 
 struct SmoothDev {
     int B, nlevels;
+    float* zero_ptr;       // optional: zero_n floats cleared by the first CTA (folds a tiny memset of the NEXT kernel's
+    int zero_n;            // accumulator into this launch; stream order makes it visible)
     SmoothLevel lv[TDL_MAX_SCALES];
 };
 
@@ -91,6 +93,7 @@ struct FeatDev {
     float* d_disp;
     float* dP;
     // bucketed d_src gather (backward scratch; all null when the atomic scatter kernel is to be used)
+    float* dP_acc;               // [B][S][12]   dP accumulator inside the zeroed scratch header; copied to dP by the gather kernel
     float* G;                    // [B][h*w][C]  d loss / d warped value, channel-last
     int* bk_cnt;                 // [S][B][h*w]  taps registered per source pixel
     int2* bk_ent;                // [S][B][h*w][kFeatBucketCap]  (target pixel, weight bits)

@@ -353,6 +353,9 @@ __global__ void __launch_bounds__(256, 1) photo_warp_kernel(const PhotoDev p) {
     if (tid < S * 12) s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
     if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
     __syncthreads();
+    // the scoring / smoothness kernels that follow accumulate their per-image sums into p.acc: cleared here (one launch less)
+    if (blockIdx.x == 0 && b == 0)
+        for (int i = tid; i < p.nscales * p.B * 4; i += 256) p.acc[i] = 0.0;
     const int pix = blockIdx.x * 256 + tid;
     if (pix >= (int)HW) return;
     const int y = pix / W, x = pix - y * W;
