@@ -93,6 +93,14 @@ def test_argument_errors_without_a_gpu(lib, tdl):
     assert lib.tdl_feat_fwd(None, None) == -1
     assert lib.tdl_edge_smooth_fwd(None, None) == -1
     assert lib.tdl_launch_count(b"tdl_photo_fwd") == 4
+    # backward scratch of the bucketed feature gather (ABI v2): G (chunk x h*w x C floats) + buckets + overflow list, bounded
+    # by the batch chunk that keeps G L2-resident (64 MB), so it stops growing with the batch
+    assert lib.tdl_feat_bwd_scratch_bytes(0, 64, 96, 320, 2) == 0
+    assert lib.tdl_feat_bwd_scratch_bytes(1, 64, 96, 320, 5) == 0
+    one = lib.tdl_feat_bwd_scratch_bytes(1, 64, 96, 320, 2)
+    assert one >= 96 * 320 * (64 * 4 + 2 * 8 * 8 + 2 * 4)
+    eight, sixteen = lib.tdl_feat_bwd_scratch_bytes(8, 64, 96, 320, 2), lib.tdl_feat_bwd_scratch_bytes(16, 64, 96, 320, 2)
+    assert one < eight and sixteen == eight
 
 
 def test_ops_refuse_cpu_tensors(tdl):
