@@ -62,6 +62,9 @@ def parse():
                     help="convert to SyncBatchNorm like cfg_kitti_fm (syncbn = True); off by default: its ~200 tiny "
                          "collectives per step halve 2-GPU throughput (measured: 186 vs 394 images/s)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample")
+    ap.add_argument("--seed-offset", type=int, default=0,
+                    help="shifts the synthetic-data seed (rank r uses 1234 + r + offset): the sparse backward paths make the "
+                         "step time data dependent, this shows by how much")
     return ap.parse_args()
 
 
@@ -220,9 +223,12 @@ class DeviceStep:
         return sum(v.numel() * v.element_size() for v in self.host.values())
 
 
+SEED_OFFSET = 0
+
+
 def rank_seed(rank):
     """Batch sharding: every rank draws its own synthetic batch (weak scaling, no data-path collective)."""
-    return 1234 + rank
+    return 1234 + rank + SEED_OFFSET
 
 
 def max_over_ranks(ms, device, dist_on):
@@ -439,7 +445,9 @@ def main():
 
 
 def run():
+    global SEED_OFFSET
     args = parse()
+    SEED_OFFSET = args.seed_offset
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
