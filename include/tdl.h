@@ -28,6 +28,9 @@
  *       get_feature_regularization_loss mono/model/mono_fm_joint/net.py:309-330
  *   tdl_recon_fwd / tdl_recon_bwd
  *       masked img_reconstruct_loss     mono/model/mono_fm_joint_inpaint/net.py:80-91
+ *   tdl_pose_fwd / tdl_pose_bwd
+ *       transformation_from_parameters  mono/model/mono_fm/net.py:201-212 (get_translation_matrix :214-222,
+ *                                       rot_from_axisangle :224-253), called by predict_poses (net.py:142-155)
  *
  * Conventions
  *   - every tensor is fp32, NCHW, contiguous, resident in device memory; only
@@ -173,6 +176,19 @@ typedef struct tdl_recon_args {
     float* d_pred;              /* out (B,3,h,w), overwritten, backward only */
 } tdl_recon_args;
 
+/* ------------------------------------------------------------------ pose prologue (axis-angle, translation -> cam_T_cam) */
+typedef struct tdl_pose_args {
+    int32_t B;
+    int32_t invert;             /* != 0: the inverted transform the reference builds for frame ids < 0 (net.py:204-209) */
+    const float* axisangle;     /* (B,3)   PoseDecoder output axisangle[:, 0]                              */
+    const float* translation;   /* (B,3)   PoseDecoder output translation[:, 0]                            */
+    float* T;                   /* out (B,4,4) outputs[("cam_T_cam", 0, f)]                                 */
+    /* backward only */
+    const float* dT;            /* (B,4,4) upstream gradient of T                                           */
+    float* d_axisangle;         /* out (B,3), overwritten                                                   */
+    float* d_translation;       /* out (B,3), overwritten                                                   */
+} tdl_pose_args;
+
 int tdl_abi_version(void);
 const char* tdl_strerror(int code);
 /* number of CUDA kernels (not memsets) one call launches -- used by bench.py's gpu_launches */
@@ -200,6 +216,9 @@ int tdl_edge_smooth_bwd(const tdl_edge_args* args, tdl_stream_t stream);
 uint64_t tdl_recon_ws_bytes(void);
 int tdl_recon_fwd(const tdl_recon_args* args, tdl_stream_t stream);
 int tdl_recon_bwd(const tdl_recon_args* args, tdl_stream_t stream);
+
+int tdl_pose_fwd(const tdl_pose_args* args, tdl_stream_t stream);
+int tdl_pose_bwd(const tdl_pose_args* args, tdl_stream_t stream);
 
 #ifdef __cplusplus
 }

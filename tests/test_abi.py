@@ -48,6 +48,8 @@ int main(void) {
   printf("%zu %zu %zu\\n", offsetof(tdl_feat_args, tgt), offsetof(tdl_feat_args, loss), offsetof(tdl_feat_args, dP));
   printf("%zu %zu\\n", offsetof(tdl_edge_args, feature), offsetof(tdl_edge_args, d_feature));
   printf("%zu %zu %zu\\n", sizeof(tdl_recon_args), offsetof(tdl_recon_args, pred), offsetof(tdl_recon_args, d_pred));
+  printf("%zu %zu %zu %zu\\n", sizeof(tdl_pose_args), offsetof(tdl_pose_args, axisangle), offsetof(tdl_pose_args, dT),
+         offsetof(tdl_feat_args, bwd_scratch));
   return 0; }''')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
@@ -64,6 +66,8 @@ int main(void) {
     assert list(map(int, out[3].split())) == [E.feature.offset, E.d_feature.offset]
     Rc = L.ReconArgs
     assert list(map(int, out[4].split())) == [C.sizeof(Rc), Rc.pred.offset, Rc.d_pred.offset]
+    Po = L.PoseArgs
+    assert list(map(int, out[5].split())) == [C.sizeof(Po), Po.axisangle.offset, Po.dT.offset, F.bwd_scratch.offset]
 
 
 def test_argument_errors_without_a_gpu(lib, tdl):
@@ -92,6 +96,10 @@ def test_argument_errors_without_a_gpu(lib, tdl):
     assert need >= 4 * 64 * 96 + 4 * 4 * 8                           # argmin masks + accumulators at least
     assert lib.tdl_feat_fwd(None, None) == -1
     assert lib.tdl_edge_smooth_fwd(None, None) == -1
+    assert lib.tdl_pose_fwd(None, None) == -1 and lib.tdl_pose_bwd(None, None) == -1
+    pa = L.PoseArgs()
+    pa.B, pa.axisangle, pa.translation, pa.T = 0, p, p, p
+    assert lib.tdl_pose_fwd(C.byref(pa), None) == -2                 # TDL_ERR_SHAPE
     assert lib.tdl_launch_count(b"tdl_photo_fwd") == 4
     # backward scratch of the bucketed feature gather (ABI v2): G (chunk x h*w x C floats) + buckets + overflow list, bounded
     # by the batch chunk that keeps G L2-resident (64 MB), so it stops growing with the batch

@@ -70,6 +70,14 @@ class ReconArgs(C.Structure):
     ]
 
 
+class PoseArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("invert", C.c_int32),
+        ("axisangle", _vp), ("translation", _vp), ("T", _vp),
+        ("dT", _vp), ("d_axisangle", _vp), ("d_translation", _vp),
+    ]
+
+
 class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int32), ("total_ms", C.c_double)]
 
@@ -78,7 +86,7 @@ EXPORTS = ["tdl_abi_version", "tdl_strerror", "tdl_launch_count", "tdl_profile_b
            "tdl_photo_ws_bytes", "tdl_photo_fwd", "tdl_photo_bwd",
            "tdl_feat_ws_bytes", "tdl_feat_bwd_scratch_bytes", "tdl_feat_fwd", "tdl_feat_bwd",
            "tdl_edge_ws_bytes", "tdl_edge_smooth_fwd", "tdl_edge_smooth_bwd",
-           "tdl_recon_ws_bytes", "tdl_recon_fwd", "tdl_recon_bwd"]
+           "tdl_recon_ws_bytes", "tdl_recon_fwd", "tdl_recon_bwd", "tdl_pose_fwd", "tdl_pose_bwd"]
 
 _lib = None
 
@@ -117,7 +125,8 @@ def lib():
     for name, T in (("tdl_photo_fwd", PhotoArgs), ("tdl_photo_bwd", PhotoArgs),
                     ("tdl_feat_fwd", FeatArgs), ("tdl_feat_bwd", FeatArgs),
                     ("tdl_edge_smooth_fwd", EdgeArgs), ("tdl_edge_smooth_bwd", EdgeArgs),
-                    ("tdl_recon_fwd", ReconArgs), ("tdl_recon_bwd", ReconArgs)):
+                    ("tdl_recon_fwd", ReconArgs), ("tdl_recon_bwd", ReconArgs),
+                    ("tdl_pose_fwd", PoseArgs), ("tdl_pose_bwd", PoseArgs)):
         fn = getattr(L, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(T), C.c_void_p]

@@ -205,6 +205,7 @@ int tdl_launch_count(const char* entry) {
     if (!strcmp(entry, "tdl_edge_smooth_bwd")) return 1;
     if (!strcmp(entry, "tdl_recon_fwd")) return 2;        // recon_fwd, finalize
     if (!strcmp(entry, "tdl_recon_bwd")) return 1;
+    if (!strcmp(entry, "tdl_pose_fwd") || !strcmp(entry, "tdl_pose_bwd")) return 1;
     return 0;
 }
 
@@ -511,6 +512,24 @@ int tdl_recon_bwd(const tdl_recon_args* a, tdl_stream_t stream) {
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("recon_bwd", launch_recon_bwd(d, st));
+    return TDL_OK;
+}
+
+// ------------------------------------------------------------------------------------ pose prologue
+int tdl_pose_fwd(const tdl_pose_args* a, tdl_stream_t stream) {
+    if (!a || !a->axisangle || !a->translation || !a->T) return TDL_ERR_NULL;
+    if (a->B < 1) return TDL_ERR_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDL_KERNEL("pose_fwd", launch_pose_fwd(a->axisangle, a->translation, a->B, a->invert, a->T, st));
+    return TDL_OK;
+}
+
+int tdl_pose_bwd(const tdl_pose_args* a, tdl_stream_t stream) {
+    if (!a || !a->axisangle || !a->translation || !a->dT || !a->d_axisangle || !a->d_translation) return TDL_ERR_NULL;
+    if (a->B < 1) return TDL_ERR_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDL_KERNEL("pose_bwd", launch_pose_bwd(a->axisangle, a->translation, a->dT, a->B, a->invert, a->d_axisangle,
+                                           a->d_translation, st));
     return TDL_OK;
 }
 

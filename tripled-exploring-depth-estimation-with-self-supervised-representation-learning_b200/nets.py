@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .geometry import transformation_from_parameters
+from .ops import pose_transform
 from .losses import ViewSynthesisLossMixin
 from .networks import DepthDecoder, ImageDecoder, PoseDecoder, ResnetEncoder
 from .registry import MONO
@@ -34,7 +34,8 @@ class _DepthPoseNet(ViewSynthesisLossMixin, nn.Module):
                 continue
             pair = [img[f], img[0]] if f < 0 else [img[0], img[f]]
             axisangle, translation = self.PoseDecoder(self.PoseEncoder(torch.cat(pair, 1)))
-            out[("cam_T_cam", 0, f)] = transformation_from_parameters(axisangle[:, 0], translation[:, 0], invert=f < 0)
+            # mono_fm/net.py:154 transformation_from_parameters: one fused launch (tdl_pose_fwd), no CPU path
+            out[("cam_T_cam", 0, f)] = pose_transform(axisangle[:, 0], translation[:, 0], invert=f < 0)
         return out
 
     def forward(self, inputs):

@@ -13,7 +13,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import EdgeArgs, FeatArgs, PhotoArgs, ReconArgs, TDL_MAX_SCALES, TDL_MAX_SRC
+from ._lib import EdgeArgs, FeatArgs, PhotoArgs, PoseArgs, ReconArgs, TDL_MAX_SCALES, TDL_MAX_SRC
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -373,3 +373,47 @@ class MaskedReconstructionLoss(torch.autograd.Function):
         with torch.cuda.device(pred.device):
             _lib.check(L.tdl_recon_bwd(C.byref(a), _stream()), "tdl_recon_bwd")
         return None, d_pred, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+class PoseTransform(torch.autograd.Function):
+    """transformation_from_parameters (mono/model/mono_fm/net.py:201-253) in one launch:
+    forward(axisangle (B,3) | (B,1,3), translation (B,3) | (B,1,3), invert: bool) -> cam_T_cam (B,4,4)."""
+
+    @staticmethod
+    def forward(ctx, axisangle, translation, invert):
+        L = _lib.lib()
+        aa = _f32c(axisangle, "axisangle").reshape(-1, 3)
+        tr = _f32c(translation, "translation").reshape(-1, 3)
+        if aa.shape != tr.shape:
+            raise _lib.TdlError(f"axisangle {tuple(axisangle.shape)} / translation {tuple(translation.shape)} mismatch")
+        B = aa.shape[0]
+        T = torch.empty((B, 4, 4), dtype=torch.float32, device=aa.device)
+        a = PoseArgs()
+        a.B, a.invert = B, int(bool(invert))
+        a.axisangle, a.translation, a.T = aa.data_ptr(), tr.data_ptr(), T.data_ptr()
+        with torch.cuda.device(aa.device):
+            _lib.check(L.tdl_pose_fwd(C.byref(a), _stream()), "tdl_pose_fwd")
+        ctx.invert = bool(invert)
+        ctx.shapes = (axisangle.shape, translation.shape)
+        ctx.save_for_backward(aa, tr)
+        return T
+
+    @staticmethod
+    def backward(ctx, gT):
+        L = _lib.lib()
+        aa, tr = ctx.saved_tensors
+        gT = _f32c(gT, "grad")
+        d_aa, d_tr = torch.empty_like(aa), torch.empty_like(tr)
+        a = PoseArgs()
+        a.B, a.invert = aa.shape[0], int(ctx.invert)
+        a.axisangle, a.translation, a.dT = aa.data_ptr(), tr.data_ptr(), gT.data_ptr()
+        a.d_axisangle, a.d_translation = d_aa.data_ptr(), d_tr.data_ptr()
+        with torch.cuda.device(aa.device):
+            _lib.check(L.tdl_pose_bwd(C.byref(a), _stream()), "tdl_pose_bwd")
+        return d_aa.reshape(ctx.shapes[0]), d_tr.reshape(ctx.shapes[1]), None
+
+
+def pose_transform(axisangle, translation, invert=False):
+    """Drop-in for the reference's ``self.transformation_from_parameters(axisangle, translation, invert)`` on CUDA tensors."""
+    return PoseTransform.apply(axisangle, translation, invert)
