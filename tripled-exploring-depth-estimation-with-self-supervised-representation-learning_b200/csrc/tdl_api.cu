@@ -26,7 +26,7 @@ inline bool pow2_factor(int big, int small, int* fac) {
 }
 
 struct PhotoWsLayout {
-    uint64_t acc_off, j_off[TDL_MAX_SCALES], w_off[TDL_MAX_SCALES], argmin_off, work_off, total;
+    uint64_t acc_off, j_off[TDL_MAX_SCALES], w_off[TDL_MAX_SCALES], argmin_off, total;
 };
 
 PhotoWsLayout photo_layout(int B, int H, int W, int nscales, const int32_t* dh, const int32_t* dw) {
@@ -42,8 +42,6 @@ PhotoWsLayout photo_layout(int B, int H, int W, int nscales, const int32_t* dh, 
     }
     L.argmin_off = off;
     off = align_up(off + (uint64_t)nscales * B * H * W, 256);
-    L.work_off = off;                                  // backward work list: length + one id per (32x32 tile, scale, image)
-    off = align_up(off + (1 + (uint64_t)nscales * B * ((H + 31) / 32) * ((W + 31) / 32)) * sizeof(int), 256);
     L.total = off;
     return L;
 }
@@ -89,14 +87,6 @@ int check_photo(const tdl_photo_args* a, bool bwd, PhotoDev* d) {
         d->Wt[s] = reinterpret_cast<float*>(ws + L.w_off[s]);
     }
     d->argmin = reinterpret_cast<unsigned char*>(ws + L.argmin_off);
-    if (bwd) {
-        // two-pass backward (light classify / sparse kernel, then the dense kernel over a work list): needs the warps the
-        // forward materialised; TDL_PHOTO_SPARSE_MAX=0 or TDL_PHOTO_ONE_PASS keep the single-kernel backward
-        bool two_pass = getenv("TDL_PHOTO_ONE_PASS") == nullptr;
-        for (int s = 0; s < a->nscales; ++s)
-            for (int f = 0; f < a->S; ++f) two_pass = two_pass && a->warped[s][f] != nullptr;
-        d->bwd_work = two_pass ? reinterpret_cast<int*>(ws + L.work_off) : nullptr;
-    }
     d->automask = a->automask != 0;
     d->use_tma = getenv("TDL_NO_TMA") == nullptr;
     d->split_fwd = getenv("TDL_FUSED_FWD") == nullptr;
@@ -288,7 +278,6 @@ int tdl_photo_bwd(const tdl_photo_args* a, tdl_stream_t stream) {
     photo_smooth_levels(a, d, true, &sm);
     sm.zero_ptr = a->dP;                                      // dP (accumulated by photo_bwd) is cleared by smooth_bwd's first CTA
     sm.zero_n = a->B * a->S * 12;
-    sm.zero_int = d.bwd_work;                                 // ... and so is the work-list length of the two-pass backward
     TDL_KERNEL("smooth_bwd", launch_smooth_bwd(sm, st));       // writes d_disp[s] (=), the photometric kernel adds to it
     TDL_KERNEL("photo_bwd", launch_photo_bwd(d, st));
     return TDL_OK;

@@ -35,7 +35,6 @@ struct PhotoDev {
     // workspace
     double* acc;                 // [nscales][B][4]: photo sum, disp sum, smooth first, smooth second
     unsigned char* argmin;       // [nscales][B][H][W]
-    int* bwd_work;               // backward, two-pass mode: [0] = number of dense tiles, [1..] = their linear tile ids; else null
     float* J[TDL_MAX_SCALES];    // area-downsampled target (B,3,dh,dw)
     float* Wt[TDL_MAX_SCALES];   // smoothness edge weights (B,6,dh,dw)
     // backward
@@ -64,7 +63,6 @@ struct SmoothLevel {
 
 struct SmoothDev {
     int B, nlevels;
-    int* zero_int;         // optional: one int cleared by the first CTA (work-list length of the two-pass photometric backward)
     float* zero_ptr;       // optional: zero_n floats cleared by the first CTA (folds a tiny memset of the NEXT kernel's
     int zero_n;            // accumulator into this launch; stream order makes it visible)
     SmoothLevel lv[TDL_MAX_SCALES];

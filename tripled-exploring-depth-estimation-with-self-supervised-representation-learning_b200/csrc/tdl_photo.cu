@@ -686,193 +686,6 @@ TDL_DEV void window_adjoint(const float* __restrict__ xs, const float* __restric
     }
 }
 
-// window_adjoint on nine (x, y) pairs already in registers, row-major like the window
-TDL_DEV void window_adjoint_vals(const float xv[9], const float yv[9], float k, float& cA, float& cB, float& cC) {
-    float xs[9], ys[9];                       // window_adjoint<3> reads [dy * 3 + dx] around the centre element 4
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        xs[i] = xv[i];
-        ys[i] = yv[i];
-    }
-    window_adjoint<3>(xs + 4, ys + 4, k, cA, cB, cC);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Backward, first pass: one light CTA per (tile, scale) classifies the tile by its arg-min bytes and finishes the
-// EMPTY and SPARSE ones itself -- auto-masked / static regions, where a handful of windows selected a warped frame.
-// It needs no staged tiles (the nine taps of a selected window are read from global memory with reflect indexing), 28 KB of
-// shared memory and ~64 registers, so 4 x more warps are resident than in the dense kernel, whose fixed per-CTA latencies
-// dominated such tiles (113 us for the bench workload).  Tiles with more than p.sparse_max selected windows are appended
-// to a work list that the dense kernel (photo_bwd_kernel) consumes next.  Same arithmetic as the dense path per window;
-// the scatter / live-pair machinery is the one described in photo_bwd_kernel's sparse branch.
-constexpr int kSNT = 64;       // small CTAs: the work of a sparse tile occupies a few threads, what counts is tiles in flight per SM
-template <int S>
-__global__ void __launch_bounds__(kSNT) photo_bwd_sparse_kernel(const PhotoDev p) {
-    constexpr int PW = kTW + 2, PH = kTH + 2, TP = kTH * kTW;
-    extern __shared__ __align__(16) float s_G[];           // [S][3][TP]
-    __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
-    __shared__ float s_dP[TDL_MAX_SRC * 12];
-    __shared__ int s_nall, s_nlive;
-    __shared__ unsigned s_bits[TDL_MAX_SRC * TP / 32];
-    __shared__ unsigned short s_list[128], s_live[9 * 128];
-
-    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const int b = blockIdx.z / p.nscales, s = blockIdx.z - b * p.nscales;
-    const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
-    const int H = p.H, W = p.W;
-    const size_t HW = (size_t)H * W;
-    const int h = p.dh[s], w = p.dw[s];
-    const unsigned char* am = p.argmin + ((size_t)s * p.B + b) * HW;
-
-    if (tid == 0) s_nall = s_nlive = 0;
-    __syncthreads();
-    // ---- classify: windows (tile + halo 1, inside the image) whose arg-min is a warped frame
-    const int chan0 = p.automask ? S : 0;
-    for (int i = tid; i < PH * PW; i += kSNT) {
-        const int r = i / PW, c = i - r * PW;
-        const int wy = ty0 - 1 + r, wx = tx0 - 1 + c;
-        if (wy >= 0 && wy < H && wx >= 0 && wx < W) {
-            const int f = (int)am[(size_t)wy * W + wx] - chan0;
-            if (f >= 0 && f < S) {
-                const int k = atomicAdd(&s_nall, 1);
-                if (k < 128) s_list[k] = (unsigned short)(i | (f << 11));
-            }
-        }
-    }
-    __syncthreads();
-    const int n_all = s_nall;
-    if (n_all == 0) return;                                   // nothing selected (CTA-uniform)
-    if (n_all > p.sparse_max) {                               // dense tile: leave it to photo_bwd_kernel
-        if (tid == 0)
-            p.bwd_work[1 + atomicAdd(p.bwd_work, 1)] = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-        return;
-    }
-
-    const float up = __ldg(p.dlosses + s) * p.photo_coef[s] / ((float)p.B * (float)H * (float)W);
-    const float g_ssim = up * 0.85f / 3.f, g_l1 = up * 0.15f / 3.f;
-    if (tid < S * 12) {
-        s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
-        s_dP[tid] = 0.f;
-    }
-    if (tid >= 48 && tid < 48 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 48] = __ldg(p.invK + (size_t)b * 9 + tid - 48);
-    const float* s_iK = s_cam + TDL_MAX_SRC * 12;
-    for (int i = tid; i < S * 3 * TP; i += kSNT) s_G[i] = 0.f;
-    for (int i = tid; i < S * TP / 32; i += kSNT) s_bits[i] = 0u;
-    __syncthreads();
-
-    // ---- scatter: one thread per (selected window, channel)
-    for (int e = tid; e < 3 * n_all; e += kSNT) {
-        const int ent = s_list[e / 3], ch = e - (e / 3) * 3;
-        const int i = ent & 2047, f = ent >> 11;
-        const int r = i / PW, c = i - r * PW;
-        const int wy = ty0 - 1 + r, wx = tx0 - 1 + c;             // image coordinates of the window centre
-        const float* tb = p.target + ((size_t)b * 3 + ch) * HW;
-        const float* wb = p.warped[s][0];
-#pragma unroll
-        for (int k = 1; k < S; ++k)
-            if (k == f) wb = p.warped[s][k];
-        wb += ((size_t)b * 3 + ch) * HW;
-        float xv[9], yv[9];
-        int lpix[9];                                              // tile-local pixel of every tap (reflected), -1 = another tile
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                // nn.ReflectionPad2d(1): a tap outside the image IS its mirror pixel
-                const int py = reflect1(wy + dy, H), px = reflect1(wx + dx, W);
-                const int k = (dy + 1) * 3 + dx + 1;
-                xv[k] = __ldg(wb + (size_t)py * W + px);
-                yv[k] = __ldg(tb + (size_t)py * W + px);
-                const int ly = py - ty0, lx = px - tx0;
-                lpix[k] = (ly >= 0 && ly < kTH && lx >= 0 && lx < kTW) ? ly * kTW + lx : -1;
-            }
-        }
-        float cA, cB, cC;
-        window_adjoint_vals(xv, yv, g_ssim * (1.f / 9.f), cA, cB, cC);
-        float* Gf = s_G + (f * 3 + ch) * TP;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            if (lpix[k] >= 0) {
-                atomicAdd(&Gf[lpix[k]], cA + 2.f * xv[k] * cB + yv[k] * cC);
-                if (ch == 0 && !(atomicOr(&s_bits[f * (TP / 32) + (lpix[k] >> 5)], 1u << (lpix[k] & 31)) & (1u << (lpix[k] & 31))))
-                    s_live[atomicAdd(&s_nlive, 1)] = (unsigned short)(lpix[k] | (f << 11));
-            }
-        }
-        if (lpix[4] >= 0) {                                       // robust-L1 term of the centre pixel
-            const float df = xv[4] - yv[4];
-            atomicAdd(&Gf[lpix[4]], g_l1 * df * rsqrt_approx(df * df + kL1Eps2));
-        }
-    }
-    __syncthreads();
-
-    // ---- chain: one thread per live (frame, pixel) pair
-    const int n_act = s_nlive;
-    const DepthParams dp{p.min_disp, p.range};
-    const float* db = p.disp[s] + (size_t)b * h * w;
-    float* dd = p.d_disp[s] + (size_t)b * h * w;
-    for (int e0 = wrp * 32; e0 < n_act; e0 += kSNT) {              // warp-uniform trip count: the dP reduction is warp-wide
-        const int e = e0 + lane;
-        const bool on = e < n_act;
-        const int ent = on ? s_live[e] : 0, i = ent & 2047, f = ent >> 11;
-        const int ly = i / kTW, lx = i - ly * kTW;
-        const int py = ty0 + ly, px = tx0 + lx;
-        const float* Pf = s_cam + f * 12;
-        const float* sbase = p.src[0];
-#pragma unroll
-        for (int k = 1; k < S; ++k)
-            if (k == f) sbase = p.src[k];
-        sbase += (size_t)b * 3 * HW;
-        const UpTap ut = up_tap(py, px, p.sy[s], p.sx[s], h, w);
-        const Geo g = backproject(up_value(db, w, ut), dp, s_iK, px, py);
-        const Proj pr = project<true>(g, Pf, H, W, p.align_corners);
-        const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
-        const float* q = sbase + (size_t)bt.y0 * W + bt.x0;
-        const int dx = bt.vx ? 1 : 0, dy = bt.vy ? W : 0;
-        float gix = 0.f, giy = 0.f;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float v00 = __ldg(q + ch * HW), v01 = bt.vx ? __ldg(q + ch * HW + dx) : 0.f;
-            const float v10 = bt.vy ? __ldg(q + ch * HW + dy) : 0.f;
-            const float v11 = (bt.vx && bt.vy) ? __ldg(q + ch * HW + dy + dx) : 0.f;
-            const float dix = -v00 * bt.ey + v01 * bt.ey - v10 * bt.ay + v11 * bt.ay;
-            const float diy = -v00 * bt.ex - v01 * bt.ax + v10 * bt.ex + v11 * bt.ax;
-            const float Gc = on ? s_G[(f * 3 + ch) * TP + i] : 0.f;
-            gix += Gc * dix;
-            giy += Gc * diy;
-        }
-        const float gu = gix * pr.mx, gv = giy * pr.my;
-        const float rz = __frcp_rn(pr.z);
-        const float gp0 = gu * rz, gp1 = gv * rz, gp2 = -(gu * pr.u + gv * pr.v) * rz;
-        float aP[12];
-        aP[0] = gp0 * g.X0; aP[1] = gp0 * g.X1; aP[2] = gp0 * g.X2; aP[3] = gp0;
-        aP[4] = gp1 * g.X0; aP[5] = gp1 * g.X1; aP[6] = gp1 * g.X2; aP[7] = gp1;
-        aP[8] = gp2 * g.X0; aP[9] = gp2 * g.X1; aP[10] = gp2 * g.X2; aP[11] = gp2;
-#pragma unroll 1
-        for (int ff = 0; ff < S; ++ff) {                          // 12-value warp reduction per frame, one shared atomic per value
-            float a2[12];
-#pragma unroll
-            for (int k = 0; k < 12; ++k) a2[k] = (on && f == ff) ? aP[k] : 0.f;
-            float tot;
-            const int slot = warp_sum12(a2, tot);
-            if (slot >= 0 && tot != 0.f) atomicAdd(&s_dP[ff * 12 + slot], tot);
-        }
-        if (on && (gp0 != 0.f || gp1 != 0.f || gp2 != 0.f)) {
-            const float gX0 = Pf[0] * gp0 + Pf[4] * gp1 + Pf[8] * gp2;
-            const float gX1 = Pf[1] * gp0 + Pf[5] * gp1 + Pf[9] * gp2;
-            const float gX2 = Pf[2] * gp0 + Pf[6] * gp1 + Pf[10] * gp2;
-            const float gD = gX0 * g.r0 + gX1 * g.r1 + gX2 * g.r2;
-            const float gdisp = -p.range * g.D * g.D * gD;
-            const float hy = 1.f - ut.ly, hx = 1.f - ut.lx;       // adjoint of the bilinear up-sampling, straight to d_disp_s
-            atomicAdd(dd + (size_t)ut.y0 * w + ut.x0, hy * hx * gdisp);
-            atomicAdd(dd + (size_t)ut.y0 * w + ut.x1, hy * ut.lx * gdisp);
-            atomicAdd(dd + (size_t)ut.y1 * w + ut.x0, ut.ly * hx * gdisp);
-            atomicAdd(dd + (size_t)ut.y1 * w + ut.x1, ut.ly * ut.lx * gdisp);
-        }
-    }
-    __syncthreads();
-    if (tid < S * 12 && s_dP[tid] != 0.f) atomicAdd(p.dP + ((size_t)b * S) * 12 + tid, s_dP[tid]);
-}
-
 // ------------------------------------------------------------------------------------------------
 // Backward.
 // Backward tile: halo 2 in y, and in x a left margin of 4 so that the TMA box starts on a 16-byte boundary
@@ -900,18 +713,8 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     __shared__ float s_tlx[kTW], s_tly[kTH];
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    // tile of this CTA: straight from the grid, or -- when photo_bwd_sparse_kernel ran first -- an entry of the work list of
-    // the tiles it left for the dense path (CTAs beyond the list length exit at once)
-    int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
-    if (p.bwd_work) {
-        if ((int)blockIdx.x >= p.bwd_work[0]) return;
-        const int lin = p.bwd_work[1 + blockIdx.x], gx_ = (p.W + kTW - 1) / kTW, gy_ = (p.H + kTH - 1) / kTH;
-        bx = lin % gx_;
-        by = (lin / gx_) % gy_;
-        bz = lin / (gx_ * gy_);
-    }
-    const int b = bz / p.nscales, s = bz - b * p.nscales;
-    const int tx0 = bx * kTW, ty0 = by * kTH;
+    const int b = blockIdx.z / p.nscales, s = blockIdx.z - b * p.nscales;
+    const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
     const int H = p.H, W = p.W;
     const size_t HW = (size_t)H * W;
     const int h = p.dh[s], w = p.dw[s];
@@ -1471,22 +1274,6 @@ static cudaError_t launch_bwd_k(const PhotoDev& p, const PhotoMaps& maps, cudaSt
         attr_done = true;
     }
     dim3 grid((p.W + kTW - 1) / kTW, (p.H + kTH - 1) / kTH, p.B * p.nscales);
-    if (p.bwd_work) {
-        // pass 1: the light kernel finishes the empty / sparse tiles and lists the dense ones; pass 2: one CTA per possible
-        // list entry (the list length is only known on the device; surplus CTAs exit at once)
-        const size_t smem1 = (size_t)S * 3 * kTH * kTW * sizeof(float);
-        static bool attr1_done = false;
-        if (!attr1_done) {
-            cudaError_t e = cudaFuncSetAttribute(photo_bwd_sparse_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-            if (e != cudaSuccess) return e;
-            attr1_done = true;
-        }
-        photo_bwd_sparse_kernel<S><<<grid, kSNT, smem1, st>>>(p);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        photo_bwd_kernel<S, kTMA><<<dim3(grid.x * grid.y * grid.z), kNT, smem, st>>>(p, maps);
-        return cudaGetLastError();
-    }
     photo_bwd_kernel<S, kTMA><<<grid, kNT, smem, st>>>(p, maps);
     return cudaGetLastError();
 }

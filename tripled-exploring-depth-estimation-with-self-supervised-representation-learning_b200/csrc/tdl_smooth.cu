@@ -134,10 +134,8 @@ TDL_DEV float nan_if_empty(float v, bool empty) { return empty ? __int_as_float(
 TDL_DEV float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
 __global__ void __launch_bounds__(kSmoothNT) smooth_bwd_kernel(const SmoothDev p) {
-    if (p.zero_ptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    if (p.zero_ptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
         for (int i = threadIdx.x; i < p.zero_n; i += kSmoothNT) p.zero_ptr[i] = 0.f;
-        if (p.zero_int && threadIdx.x == 0) *p.zero_int = 0;
-    }
     const SmoothLevel& L = p.lv[blockIdx.y];
     const int b = blockIdx.z;
     const int h = L.h, w = L.w, C = L.C;
