@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kFeatNT) feat_fwd_kernel(const FeatDev p) {
 #pragma unroll
             for (int j = 0; j < CB; ++j) {
                 const unsigned co = (unsigned)min(c0 + j, C - 1) * uhw;
-                t[j] = __ldg(tbase + (co + (unsigned)pix));
+                t[j] = __ldcs(tbase + (co + (unsigned)pix));          // read once: keep L1 for the gathers
 #pragma unroll
                 for (int f = 0; f < S; ++f) {
                     v[f][j][0] = __ldg(sbase[f] + (co + (unsigned)o00[f]));
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kFeatNT) feat_fwd_kernel(const FeatDev p) {
                         val += v[f][j][1] * bt[f].ne;
                         val += v[f][j][2] * bt[f].sw;
                         val += v[f][j][3] * bt[f].se;
-                        if (wbase[f]) wbase[f][co] = val;
+                        if (wbase[f]) __stcs(wbase[f] + co, val);
                         const float df = __fsub_rn(val, t[j]);                     // robust_l1(tgt_f, src_f)
                         acc[f] += sqrt_fast(__fadd_rn(__fmul_rn(df, df), kL1Eps2));
                     }
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(kBucketRows * 32, 1) feat_bwd_bucket_kernel(co
 #pragma unroll
         for (int j = 0; j < CB; ++j) {
             const unsigned co = (unsigned)(c0 + j) * uhw;
-            t[j] = active ? __ldg(tbase + (co + upix)) : 0.f;
+            t[j] = active ? __ldcs(tbase + (co + upix)) : 0.f;
             v[j][0] = active ? __ldg(sbb + (co + (unsigned)o00)) : 0.f;
             v[j][1] = active ? __ldg(sbb + (co + (unsigned)o01)) : 0.f;
             v[j][2] = active ? __ldg(sbb + (co + (unsigned)o10)) : 0.f;
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kBucketRows * 32, 1) feat_bwd_bucket_kernel(co
             gix += gvv * dix;
             giy += gvv * diy;
             gq[j] = gvv;
-            if (dtb && active) dtb[co + upix] = -gvv;
+            if (dtb && active) __stcs(dtb + (co + upix), -gvv);
         }
         if (active) *reinterpret_cast<float4*>(Gp + c0) = make_float4(gq[0], gq[1], gq[2], gq[3]);
     }
