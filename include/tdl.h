@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define TDL_ABI_VERSION 2
+#define TDL_ABI_VERSION 3
 #define TDL_MAX_SRC 4      /* source frames per target (frame_ids[1:])       */
 #define TDL_MAX_SCALES 4   /* disparity scales (opt.scales)                  */
 
@@ -62,6 +62,14 @@ extern "C" {
 #define TDL_ERR_WORKSPACE (-3) /* workspace_bytes smaller than *_ws_bytes()   */
 #define TDL_ERR_COUNT (-4)     /* S / nscales / C out of range                */
 #define TDL_ERR_NODEVICE (-5)  /* no CUDA device / not sm_100                 */
+#define TDL_ERR_OPTION (-6)    /* tdl_set_option / tdl_get_option: unknown name */
+
+/* storage of the feature maps handed to tdl_feat_* (arithmetic is fp32 in registers either way)            */
+#define TDL_LAYOUT_NCHW 0      /* (B,C,h,w) contiguous: what the reference's extractor returns               */
+#define TDL_LAYOUT_NHWC 1      /* (B,h,w,C) contiguous: torch channels_last memory of a (B,C,h,w) tensor --
+                                  one bilinear tap is one contiguous C-vector (256 B at C=64 fp32)             */
+#define TDL_DTYPE_F32 0
+#define TDL_DTYPE_BF16 1       /* opt-in storage mode (north_star "bf16/fp32 loads"); never the parity config */
 
 typedef void* tdl_stream_t;    /* a cudaStream_t */
 
@@ -109,16 +117,19 @@ typedef struct tdl_feat_args {
     int32_t S;
     int32_t disp_h, disp_w;     /* disp is (B,1,disp_h,disp_w), resized bilinearly to (h,w)            */
     int32_t align_corners;
+    int32_t layout;             /* TDL_LAYOUT_*: of tgt, src, warped, d_tgt, d_src (all the same)       */
+    int32_t dtype;              /* TDL_DTYPE_*:  of tgt, src, warped, d_tgt, d_src (all the same);
+                                   NHWC requires C % 8 == 0; BF16 requires NHWC                          */
     double min_depth, max_depth;
     float coef;                 /* loss = coef * mean_{b,y,x} min_f mean_c robust_l1                    */
     float reserved0;
 
-    const float* tgt;                        /* (B,C,h,w)  extractor(color_0)[0]                       */
-    const float* src[TDL_MAX_SRC];           /* (B,C,h,w)  extractor(color_f)[0]                       */
+    const void* tgt;                         /* (B,C,h,w)  extractor(color_0)[0]      (float or bf16)   */
+    const void* src[TDL_MAX_SRC];            /* (B,C,h,w)  extractor(color_f)[0]                       */
     const float* disp;
     const float* P;                          /* (B,S,3,4) built from the half-resolution K            */
     const float* invK;                       /* (B,3,3)   pinv(K_half)[:, :3, :3]                      */
-    float* warped[TDL_MAX_SRC];              /* out, optional: outputs[("feature",f,0)]               */
+    void* warped[TDL_MAX_SRC];               /* out, optional: outputs[("feature",f,0)]               */
     int64_t* min_index;                      /* out, optional (B,h,w)                                  */
     void* workspace;
     uint64_t workspace_bytes;
@@ -126,8 +137,8 @@ typedef struct tdl_feat_args {
 
     /* backward only */
     const float* dloss;         /* [1] */
-    float* d_tgt;               /* out, optional (B,C,h,w), overwritten                                 */
-    float* d_src[TDL_MAX_SRC];  /* out, optional (all or none), overwritten (zero where not selected)   */
+    void* d_tgt;                /* out, optional (B,C,h,w), overwritten                                 */
+    void* d_src[TDL_MAX_SRC];   /* out, optional (all or none), overwritten (zero where not selected)   */
     float* d_disp;              /* out (B,1,disp_h,disp_w), overwritten                                 */
     float* dP;                  /* out (B,S,3,4), overwritten                                           */
     void* bwd_scratch;          /* optional, >= tdl_feat_bwd_scratch_bytes(): lets the d_src scatter of
@@ -191,6 +202,12 @@ typedef struct tdl_pose_args {
 
 int tdl_abi_version(void);
 const char* tdl_strerror(int code);
+/* Process-wide switches for tests and kernel experiments (the defaults are the product path).  They are
+ * initialised once from the environment (TDL_NO_TMA, TDL_FUSED_FWD, TDL_PHOTO_SPARSE_MAX, TDL_FEAT_ATOMIC,
+ * TDL_FEAT_CHUNK) and afterwards only change through this call -- the entry points never call getenv().
+ * Names: "no_tma", "fused_fwd", "photo_sparse_max", "feat_atomic", "feat_chunk". */
+int tdl_set_option(const char* name, int value);
+int tdl_get_option(const char* name, int* value);
 /* number of CUDA kernels (not memsets) one call launches -- used by bench.py's gpu_launches */
 int tdl_launch_count(const char* entry_point);
 

@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol(lib, tdl):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/tdl.h but not exported by libtdl.so"
     assert sorted(tdl._lib.EXPORTS) == names
-    assert lib.tdl_abi_version() == 2
+    assert lib.tdl_abi_version() == tdl._lib.TDL_ABI_VERSION == 3
     assert lib.tdl_strerror(0) == b"ok"
     assert b"NULL" in lib.tdl_strerror(-1)
 
@@ -45,7 +45,8 @@ int main(void) {
   printf("%zu %zu %zu %zu\\n", sizeof(tdl_photo_args), sizeof(tdl_feat_args), sizeof(tdl_edge_args), sizeof(tdl_kernel_time));
   printf("%zu %zu %zu %zu %zu\\n", offsetof(tdl_photo_args, min_depth), offsetof(tdl_photo_args, target),
          offsetof(tdl_photo_args, noise), offsetof(tdl_photo_args, losses), offsetof(tdl_photo_args, dP));
-  printf("%zu %zu %zu\\n", offsetof(tdl_feat_args, tgt), offsetof(tdl_feat_args, loss), offsetof(tdl_feat_args, dP));
+  printf("%zu %zu %zu %zu %zu\\n", offsetof(tdl_feat_args, tgt), offsetof(tdl_feat_args, loss), offsetof(tdl_feat_args, dP),
+         offsetof(tdl_feat_args, layout), offsetof(tdl_feat_args, dtype));
   printf("%zu %zu\\n", offsetof(tdl_edge_args, feature), offsetof(tdl_edge_args, d_feature));
   printf("%zu %zu %zu\\n", sizeof(tdl_recon_args), offsetof(tdl_recon_args, pred), offsetof(tdl_recon_args, d_pred));
   printf("%zu %zu %zu %zu\\n", sizeof(tdl_pose_args), offsetof(tdl_pose_args, axisangle), offsetof(tdl_pose_args, dT),
@@ -61,7 +62,7 @@ int main(void) {
     assert list(map(int, out[1].split())) == [P.min_depth.offset, P.target.offset, P.noise.offset, P.losses.offset,
                                               P.dP.offset]
     F = L.FeatArgs
-    assert list(map(int, out[2].split())) == [F.tgt.offset, F.loss.offset, F.dP.offset]
+    assert list(map(int, out[2].split())) == [F.tgt.offset, F.loss.offset, F.dP.offset, F.layout.offset, F.dtype.offset]
     E = L.EdgeArgs
     assert list(map(int, out[3].split())) == [E.feature.offset, E.d_feature.offset]
     Rc = L.ReconArgs
@@ -101,6 +102,22 @@ def test_argument_errors_without_a_gpu(lib, tdl):
     pa.B, pa.axisangle, pa.translation, pa.T = 0, p, p, p
     assert lib.tdl_pose_fwd(C.byref(pa), None) == -2                 # TDL_ERR_SHAPE
     assert lib.tdl_launch_count(b"tdl_photo_fwd") == 4
+    # valid arguments but no sm_100 device behind the call: TDL_ERR_NODEVICE, never a raw cudaError / a launch
+    import torch
+    if not torch.cuda.is_available():
+        pa.B = 1
+        assert lib.tdl_pose_fwd(C.byref(pa), None) == -5
+        assert b"sm_100" in lib.tdl_strerror(-5)
+    # option switches (replace the per-call getenv of ABI v2)
+    v = C.c_int(-1)
+    assert lib.tdl_get_option(b"photo_sparse_max", C.byref(v)) == 0 and v.value == 128
+    assert lib.tdl_set_option(b"photo_sparse_max", 16) == 0
+    assert lib.tdl_get_option(b"photo_sparse_max", C.byref(v)) == 0 and v.value == 16
+    assert lib.tdl_set_option(b"photo_sparse_max", 128) == 0
+    assert lib.tdl_set_option(b"no_such_option", 1) == -6 and lib.tdl_set_option(None, 1) == -1
+    with L.options(no_tma=1):
+        assert L.get_option("no_tma") == 1
+    assert L.get_option("no_tma") == 0
     # backward scratch of the bucketed feature gather (ABI v2): G (chunk x h*w x C floats) + buckets + overflow list, bounded
     # by the batch chunk that keeps G L2-resident (64 MB), so it stops growing with the batch
     assert lib.tdl_feat_bwd_scratch_bytes(0, 64, 96, 320, 2) == 0

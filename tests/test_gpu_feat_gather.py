@@ -1,5 +1,5 @@
 """GPU: the bucketed-gather backward of the feature-metric loss (feat_bwd_bucket + feat_gather + feat_overflow kernels)
-against the atomic-scatter kernel of the same library (TDL_FEAT_ATOMIC=1) on inputs chosen to stress it:
+against the atomic-scatter kernel of the same library (library option feat_atomic = 1) on inputs chosen to stress it:
 
   * pixel-level noisy disparity -> sampling points scattered by many pixels (buckets of very different sizes);
   * a large translation -> most samples clip to the image border, so border buckets overflow into the overflow list;
@@ -42,16 +42,10 @@ def _run(args, atomic):
     leaves = [t.to(dev).clone().requires_grad_(True) for t in (tgt, disp, P)] + \
              [t.to(dev).clone().requires_grad_(True) for t in srcs]
     cfg = tdl.ops.FeatConfig(n_src=len(srcs), coef=1.0)
-    if atomic:
-        os.environ["TDL_FEAT_ATOMIC"] = "1"
-    else:
-        os.environ.pop("TDL_FEAT_ATOMIC", None)
-    try:
+    with tdl._lib.options(feat_atomic=int(atomic)):
         res = tdl.ops.FeatureMetricLoss.apply(cfg, leaves[0], leaves[1], leaves[2], invK.to(dev), *leaves[3:])
         res[0].sum().backward()
         torch.cuda.synchronize()
-    finally:
-        os.environ.pop("TDL_FEAT_ATOMIC", None)
     return float(res[0].detach()), [t.grad.detach().cpu() for t in leaves]
 
 
@@ -78,21 +72,21 @@ def test_bucketed_gather_matches_atomic_scatter(B, C, h, w, S, shift):
             assert rel_l2(gb, ga) < 1e-5, (name, rel_l2(gb, ga))
 
 
-def test_batch_chunking_is_invisible(monkeypatch):
+def test_batch_chunking_is_invisible():
     """The bucketed backward runs in batch chunks (G stays L2-resident); chunk sizes that do not divide the batch and a
     chunk of one image must give the same gradients as the un-chunked run."""
     args = _inputs(5, 8, 40, 64, 2, 4200, 0.05)
-    monkeypatch.delenv("TDL_FEAT_CHUNK", raising=False)
-    loss0, grads0 = _run(args, atomic=False)
-    for chunk in ("2", "1", "4"):
-        monkeypatch.setenv("TDL_FEAT_CHUNK", chunk)
-        loss1, grads1 = _run(args, atomic=False)
+    with pkg()._lib.options(feat_chunk=0):
+        loss0, grads0 = _run(args, atomic=False)
+    for chunk in (2, 1, 4):
+        with pkg()._lib.options(feat_chunk=chunk):
+            loss1, grads1 = _run(args, atomic=False)
         assert loss1 == loss0
         for g0, g1 in zip(grads0, grads1):
             assert rel_l2(g1, g0) < 1e-6, chunk
 
 
-def test_gather_path_without_scratch_falls_back(monkeypatch):
+def test_gather_path_without_scratch_falls_back():
     """C % 4 != 0 cannot use the 16-byte G rows: the library must silently take the atomic kernel, same results."""
     args = _inputs(1, 6, 32, 48, 2, 4100, 0.0)
     loss_a, grads_a = _run(args, atomic=True)

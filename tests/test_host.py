@@ -75,15 +75,34 @@ def test_synth_is_deterministic(tdl):
 
 
 def test_loss_dict_total(tdl):
+    """total() == sum of .mean() of every entry (mono/apis/trainer.py:39-48), whether an entry is covered by a
+    fused-kernel part or was appended the reference's way."""
     d = tdl.losses.LossDict()
     v = torch.tensor([1.0, 2.0, 3.0])
-    d.add_part(v)
-    d.add_part(torch.tensor(0.5), 4)
-    d["a"], d["b"] = v[0], v[1]
+    d["a"], d["b"], d["c"] = v[0], v[1], v[2]
+    d.add_part(v, 1, ["a", "b", "c"])
+    per = torch.tensor(0.5)
+    for s in range(4):
+        d[("p", s)] = per
+    d.add_part(per, 4, [("p", s) for s in range(4)])
     assert float(d.total()) == 8.0
+    # entries added like the reference does (loss_dict.update(self.compute_xxx_loss(...)), loss_dict[k] = v)
+    d.update({"extra": torch.tensor([[1.0, 3.0]])})          # un-reduced map: batch_processor takes its mean
+    d["more"] = torch.tensor(0.25)
+    assert float(d.total()) == 8.0 + 2.0 + 0.25
+    assert float(d.total()) == float(sum(x.mean() for x in d.values()))
+    # overwriting a covered entry drops the part; the remaining views are summed one by one
+    d["a"] = torch.tensor(10.0)
+    assert float(d.total()) == float(sum(x.mean() for x in d.values()))
+    del d["b"]
+    assert float(d.total()) == float(sum(x.mean() for x in d.values()))
     e = tdl.losses.LossDict()
     e["x"] = torch.tensor(2.0)
     assert float(e.total()) == 2.0
+    f = tdl.losses.LossDict()
+    f["y"] = torch.tensor(1.0)
+    f.absorb(d)
+    assert float(f.total()) == 1.0 + float(d.total())
 
 
 def test_algorithmic_bytes_match_survey():

@@ -10,7 +10,9 @@ LIB_PATH = os.environ.get("TDL_LIB_PATH") or os.path.join(HERE, "libtdl.so")   #
 
 TDL_MAX_SRC = 4
 TDL_MAX_SCALES = 4
-TDL_ABI_VERSION = 2
+TDL_ABI_VERSION = 3
+TDL_LAYOUT_NCHW, TDL_LAYOUT_NHWC = 0, 1
+TDL_DTYPE_F32, TDL_DTYPE_BF16 = 0, 1
 
 _fp = C.POINTER(C.c_float)
 _vp = C.c_void_p
@@ -40,6 +42,7 @@ class FeatArgs(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("C", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("S", C.c_int32),
         ("disp_h", C.c_int32), ("disp_w", C.c_int32), ("align_corners", C.c_int32),
+        ("layout", C.c_int32), ("dtype", C.c_int32),
         ("min_depth", C.c_double), ("max_depth", C.c_double),
         ("coef", C.c_float), ("reserved0", C.c_float),
         ("tgt", _vp), ("src", _vp * TDL_MAX_SRC), ("disp", _vp), ("P", _vp), ("invK", _vp),
@@ -82,7 +85,7 @@ class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int32), ("total_ms", C.c_double)]
 
 
-EXPORTS = ["tdl_abi_version", "tdl_strerror", "tdl_launch_count", "tdl_profile_begin", "tdl_profile_end",
+EXPORTS = ["tdl_abi_version", "tdl_strerror", "tdl_set_option", "tdl_get_option", "tdl_launch_count", "tdl_profile_begin", "tdl_profile_end",
            "tdl_photo_ws_bytes", "tdl_photo_fwd", "tdl_photo_bwd",
            "tdl_feat_ws_bytes", "tdl_feat_bwd_scratch_bytes", "tdl_feat_fwd", "tdl_feat_bwd",
            "tdl_edge_ws_bytes", "tdl_edge_smooth_fwd", "tdl_edge_smooth_bwd",
@@ -109,6 +112,10 @@ def lib():
     L.tdl_strerror.argtypes = [C.c_int]
     L.tdl_launch_count.restype = C.c_int
     L.tdl_launch_count.argtypes = [C.c_char_p]
+    L.tdl_set_option.restype = C.c_int
+    L.tdl_set_option.argtypes = [C.c_char_p, C.c_int]
+    L.tdl_get_option.restype = C.c_int
+    L.tdl_get_option.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
     L.tdl_profile_begin.restype = C.c_int
     L.tdl_profile_end.restype = C.c_int
     L.tdl_profile_end.argtypes = [C.POINTER(KernelTime), C.c_int]
@@ -139,6 +146,34 @@ def lib():
 def check(rc, what):
     if rc != 0:
         raise TdlError(f"{what} failed ({rc}): {lib().tdl_strerror(rc).decode()}")
+
+
+def set_option(name: str, value: int) -> None:
+    """Process-wide kernel-selection switch (tests / experiments): include/tdl.h tdl_set_option."""
+    check(lib().tdl_set_option(name.encode(), int(value)), f"tdl_set_option({name})")
+
+
+def get_option(name: str) -> int:
+    v = C.c_int(0)
+    check(lib().tdl_get_option(name.encode(), C.byref(v)), f"tdl_get_option({name})")
+    return v.value
+
+
+class options:
+    """with options(photo_sparse_max=0, no_tma=1): ...   -- restores the previous values on exit."""
+
+    def __init__(self, **kw):
+        self.kw, self.old = kw, {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.old[k] = get_option(k)
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)
 
 
 def launch_count(entry: str) -> int:

@@ -4,7 +4,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -14,6 +16,48 @@
 using namespace tdl;
 
 namespace {
+
+// ---- process-wide tuning / test switches.  Read from the environment ONCE (first use) and afterwards only changed through
+// tdl_set_option(): the entry points below are on the training step's host path and must not call getenv().
+enum Opt { kOptNoTma = 0, kOptFusedFwd, kOptSparseMax, kOptFeatAtomic, kOptFeatChunk, kOptCount };
+const char* const kOptNames[kOptCount] = {"no_tma", "fused_fwd", "photo_sparse_max", "feat_atomic", "feat_chunk"};
+const char* const kOptEnv[kOptCount] = {"TDL_NO_TMA", "TDL_FUSED_FWD", "TDL_PHOTO_SPARSE_MAX", "TDL_FEAT_ATOMIC", "TDL_FEAT_CHUNK"};
+const int kOptDefault[kOptCount] = {0, 0, 128, 0, 0};
+std::atomic<int> g_opt[kOptCount];
+std::once_flag g_opt_once;
+
+void init_options() {
+    for (int i = 0; i < kOptCount; ++i) {
+        const char* e = getenv(kOptEnv[i]);
+        int v = kOptDefault[i];
+        if (e) v = (i == kOptSparseMax || i == kOptFeatChunk) ? atoi(e) : 1;
+        g_opt[i].store(v, std::memory_order_relaxed);
+    }
+}
+inline int opt(Opt o) {
+    std::call_once(g_opt_once, init_options);
+    return g_opt[o].load(std::memory_order_relaxed);
+}
+
+// The kernels are sm_100a binaries: any other device (or none) is reported as TDL_ERR_NODEVICE instead of the raw
+// cudaErrorNoKernelImageForDevice of the first launch.  The capability is looked up once per device.
+int check_device() {
+    static std::atomic<int> cc_major[64];
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) {
+        cudaGetLastError();
+        return TDL_ERR_NODEVICE;
+    }
+    int major = dev < 64 ? cc_major[dev].load(std::memory_order_relaxed) : 0;
+    if (major == 0) {
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+            cudaGetLastError();
+            return TDL_ERR_NODEVICE;
+        }
+        if (dev < 64) cc_major[dev].store(major, std::memory_order_relaxed);
+    }
+    return major == 10 ? TDL_OK : TDL_ERR_NODEVICE;
+}
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
@@ -88,13 +132,12 @@ int check_photo(const tdl_photo_args* a, bool bwd, PhotoDev* d) {
     }
     d->argmin = reinterpret_cast<unsigned char*>(ws + L.argmin_off);
     d->automask = a->automask != 0;
-    d->use_tma = getenv("TDL_NO_TMA") == nullptr;
-    d->split_fwd = getenv("TDL_FUSED_FWD") == nullptr;
+    d->use_tma = !opt(kOptNoTma);
+    d->split_fwd = !opt(kOptFusedFwd);
     {
         // tiles with <= 128 selected windows (of 1156 incl. halo, all frames) take the scatter path; 128 is also the hard
         // limit (9 live pixels per window must fit the tile's list).  Tests: 0 forces the dense backward everywhere.
-        const char* e = getenv("TDL_PHOTO_SPARSE_MAX");
-        const int v = e ? atoi(e) : 128;
+        const int v = opt(kOptSparseMax);
         d->sparse_max = v < 0 ? 0 : (v > 128 ? 128 : v);
     }
     d->align_corners = a->align_corners != 0;
@@ -138,7 +181,8 @@ struct ProfRec {
     cudaEvent_t a, b;
 };
 struct Profiler {
-    bool on = false;
+    std::atomic<bool> on{false};
+    std::mutex mu;                       // guards recs / pool: entry points may be called from several host threads
     std::vector<ProfRec> recs;
     std::vector<cudaEvent_t> pool;
     cudaEvent_t get() {
@@ -156,15 +200,18 @@ struct Profiler {
 struct ProfScope {
     cudaStream_t st;
     bool active;
-    ProfScope(const char* name, cudaStream_t s) : st(s), active(g_prof.on) {
+    cudaEvent_t end = nullptr;
+    ProfScope(const char* name, cudaStream_t s) : st(s), active(g_prof.on.load(std::memory_order_relaxed)) {
         if (active) {
+            std::lock_guard<std::mutex> lk(g_prof.mu);
             ProfRec r{name, g_prof.get(), g_prof.get()};
+            end = r.b;
             cudaEventRecord(r.a, st);
             g_prof.recs.push_back(r);
         }
     }
     ~ProfScope() {
-        if (active) cudaEventRecord(g_prof.recs.back().b, st);
+        if (active) cudaEventRecord(end, st);
     }
 };
 
@@ -188,10 +235,32 @@ const char* tdl_strerror(int code) {
         case TDL_ERR_SHAPE: return "tdl: unsupported shape (disp size must divide the image size by a power of two <= 32)";
         case TDL_ERR_WORKSPACE: return "tdl: workspace too small (see *_ws_bytes)";
         case TDL_ERR_COUNT: return "tdl: S / nscales / C out of range";
-        case TDL_ERR_NODEVICE: return "tdl: no CUDA device";
+        case TDL_ERR_NODEVICE: return "tdl: no CUDA device, or the current device is not sm_100 (B200): there is no other code path";
+        case TDL_ERR_OPTION: return "tdl: unknown option name";
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "tdl: unknown error";
+}
+
+int tdl_set_option(const char* name, int value) {
+    if (!name) return TDL_ERR_NULL;
+    for (int i = 0; i < kOptCount; ++i)
+        if (!strcmp(name, kOptNames[i])) {
+            opt((Opt)i);                                   // make sure the environment defaults were read first
+            g_opt[i].store(value, std::memory_order_relaxed);
+            return TDL_OK;
+        }
+    return TDL_ERR_OPTION;
+}
+
+int tdl_get_option(const char* name, int* value) {
+    if (!name || !value) return TDL_ERR_NULL;
+    for (int i = 0; i < kOptCount; ++i)
+        if (!strcmp(name, kOptNames[i])) {
+            *value = opt((Opt)i);
+            return TDL_OK;
+        }
+    return TDL_ERR_OPTION;
 }
 
 int tdl_launch_count(const char* entry) {
@@ -218,6 +287,7 @@ int tdl_profile_begin(void) {
 // (name, launches, total milliseconds).  Returns the number of rows; profiling is switched off.
 int tdl_profile_end(tdl_kernel_time* out, int max_entries) {
     g_prof.on = false;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
     std::map<std::string, std::pair<int, double>> agg;
     std::vector<std::string> order;
     for (ProfRec& r : g_prof.recs) {
@@ -252,7 +322,8 @@ uint64_t tdl_photo_ws_bytes(int32_t B, int32_t H, int32_t W, int32_t S, int32_t 
 
 int tdl_photo_fwd(const tdl_photo_args* a, tdl_stream_t stream) {
     PhotoDev d;
-    const int rc = check_photo(a, false, &d);
+    int rc = check_photo(a, false, &d);
+    if (rc == TDL_OK) rc = check_device();
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (photo_fwd_can_split(d)) {                             // (photo_warp clears the accumulators itself)
@@ -271,7 +342,8 @@ int tdl_photo_fwd(const tdl_photo_args* a, tdl_stream_t stream) {
 
 int tdl_photo_bwd(const tdl_photo_args* a, tdl_stream_t stream) {
     PhotoDev d;
-    const int rc = check_photo(a, true, &d);
+    int rc = check_photo(a, true, &d);
+    if (rc == TDL_OK) rc = check_device();
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SmoothDev sm;
@@ -301,7 +373,7 @@ static int feat_chunk_images(int B, int C, int h, int w) {
     const uint64_t per_image = (uint64_t)h * w * C * sizeof(float);
     const uint64_t budget = 64ull << 20;
     uint64_t n = per_image ? budget / per_image : 1;
-    if (const char* e = getenv("TDL_FEAT_CHUNK")) n = (uint64_t)atoi(e);      // tests: force small chunks
+    if (const int forced = opt(kOptFeatChunk)) n = (uint64_t)forced;         // tests: force small chunks
     if (n < 1) n = 1;
     return (int)(n < (uint64_t)B ? n : (uint64_t)B);
 }
@@ -341,13 +413,14 @@ static int check_feat(const tdl_feat_args* a, bool bwd, FeatDev* d) {
     d->min_disp = (float)(1.0 / a->max_depth);
     d->range = (float)(1.0 / a->min_depth - 1.0 / a->max_depth);
     d->coef = a->coef;
-    d->tgt = a->tgt; d->disp = a->disp; d->P = a->P; d->invK = a->invK;
+    if (a->layout != TDL_LAYOUT_NCHW || a->dtype != TDL_DTYPE_F32) return TDL_ERR_SHAPE;
+    d->tgt = static_cast<const float*>(a->tgt); d->disp = a->disp; d->P = a->P; d->invK = a->invK;
     int n_dsrc = 0;
     for (int f = 0; f < a->S; ++f) {
         if (!a->src[f]) return TDL_ERR_NULL;
-        d->src[f] = a->src[f];
-        d->warped[f] = a->warped[f];
-        d->d_src[f] = a->d_src[f];
+        d->src[f] = static_cast<const float*>(a->src[f]);
+        d->warped[f] = static_cast<float*>(a->warped[f]);
+        d->d_src[f] = static_cast<float*>(a->d_src[f]);
         n_dsrc += a->d_src[f] != nullptr;
     }
     if (bwd && n_dsrc != 0 && n_dsrc != a->S) return TDL_ERR_NULL;     // all or none
@@ -358,10 +431,10 @@ static int check_feat(const tdl_feat_args* a, bool bwd, FeatDev* d) {
     d->loss = a->loss;
     if (bwd) {
         if (!a->dloss || !a->d_disp || !a->dP) return TDL_ERR_NULL;
-        d->dloss = a->dloss; d->d_tgt = a->d_tgt; d->d_disp = a->d_disp; d->dP = a->dP;
+        d->dloss = a->dloss; d->d_tgt = static_cast<float*>(a->d_tgt); d->d_disp = a->d_disp; d->dP = a->dP;
         const FeatScratchLayout L = feat_scratch_layout(a->B, a->C, a->h, a->w, a->S);
         if (n_dsrc == a->S && a->bwd_scratch && a->bwd_scratch_bytes >= L.total && a->C % 4 == 0 && (uint64_t)a->h * a->w * a->C < (1ull << 28) &&
-            (reinterpret_cast<uintptr_t>(a->bwd_scratch) & 15) == 0 && getenv("TDL_FEAT_ATOMIC") == nullptr) {
+            (reinterpret_cast<uintptr_t>(a->bwd_scratch) & 15) == 0 && !opt(kOptFeatAtomic)) {
             char* sc = static_cast<char*>(a->bwd_scratch);
             d->ov_cnt = reinterpret_cast<int*>(sc + L.cnt_off);
             d->dP_acc = reinterpret_cast<float*>(sc + L.cnt_off + align_up((uint64_t)feat_chunk_images(a->B, a->C, a->h, a->w) * sizeof(int), 256));
@@ -376,7 +449,8 @@ static int check_feat(const tdl_feat_args* a, bool bwd, FeatDev* d) {
 
 int tdl_feat_fwd(const tdl_feat_args* a, tdl_stream_t stream) {
     FeatDev d;
-    const int rc = check_feat(a, false, &d);
+    int rc = check_feat(a, false, &d);
+    if (rc == TDL_OK) rc = check_device();
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("memset", cudaMemsetAsync(d.acc, 0, (size_t)a->B * sizeof(double), st));
@@ -387,7 +461,8 @@ int tdl_feat_fwd(const tdl_feat_args* a, tdl_stream_t stream) {
 
 int tdl_feat_bwd(const tdl_feat_args* a, tdl_stream_t stream) {
     FeatDev d;
-    const int rc = check_feat(a, true, &d);
+    int rc = check_feat(a, true, &d);
+    if (rc == TDL_OK) rc = check_device();
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t fbytes = (size_t)a->B * a->C * a->h * a->w * sizeof(float);
@@ -462,7 +537,8 @@ static int check_edge(const tdl_edge_args* a, bool bwd, SmoothDev* sm, float** J
 int tdl_edge_smooth_fwd(const tdl_edge_args* a, tdl_stream_t stream) {
     SmoothDev sm;
     float* J;
-    const int rc = check_edge(a, false, &sm, &J);
+    int rc = check_edge(a, false, &sm, &J);
+    if (rc == TDL_OK) rc = check_device();
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("memset", cudaMemsetAsync(sm.lv[0].acc, 0, (size_t)a->B * 4 * sizeof(double), st));
@@ -475,7 +551,8 @@ int tdl_edge_smooth_fwd(const tdl_edge_args* a, tdl_stream_t stream) {
 int tdl_edge_smooth_bwd(const tdl_edge_args* a, tdl_stream_t stream) {
     SmoothDev sm;
     float* J;
-    const int rc = check_edge(a, true, &sm, &J);
+    int rc = check_edge(a, true, &sm, &J);
+    if (rc == TDL_OK) rc = check_device();
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("edge_smooth_bwd", launch_smooth_bwd(sm, st));
@@ -498,7 +575,8 @@ static int check_recon(const tdl_recon_args* a, bool bwd, ReconArgsDev* d) {
 
 int tdl_recon_fwd(const tdl_recon_args* a, tdl_stream_t stream) {
     ReconArgsDev d;
-    const int rc = check_recon(a, false, &d);
+    int rc = check_recon(a, false, &d);
+    if (rc == TDL_OK) rc = check_device();
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("memset", cudaMemsetAsync(d.acc, 0, 2 * sizeof(double), st));
@@ -508,7 +586,8 @@ int tdl_recon_fwd(const tdl_recon_args* a, tdl_stream_t stream) {
 
 int tdl_recon_bwd(const tdl_recon_args* a, tdl_stream_t stream) {
     ReconArgsDev d;
-    const int rc = check_recon(a, true, &d);
+    int rc = check_recon(a, true, &d);
+    if (rc == TDL_OK) rc = check_device();
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("recon_bwd", launch_recon_bwd(d, st));
@@ -519,6 +598,7 @@ int tdl_recon_bwd(const tdl_recon_args* a, tdl_stream_t stream) {
 int tdl_pose_fwd(const tdl_pose_args* a, tdl_stream_t stream) {
     if (!a || !a->axisangle || !a->translation || !a->T) return TDL_ERR_NULL;
     if (a->B < 1) return TDL_ERR_SHAPE;
+    if (const int rc = check_device()) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("pose_fwd", launch_pose_fwd(a->axisangle, a->translation, a->B, a->invert, a->T, st));
     return TDL_OK;
@@ -527,6 +607,7 @@ int tdl_pose_fwd(const tdl_pose_args* a, tdl_stream_t stream) {
 int tdl_pose_bwd(const tdl_pose_args* a, tdl_stream_t stream) {
     if (!a || !a->axisangle || !a->translation || !a->dT || !a->d_axisangle || !a->d_translation) return TDL_ERR_NULL;
     if (a->B < 1) return TDL_ERR_SHAPE;
+    if (const int rc = check_device()) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("pose_bwd", launch_pose_bwd(a->axisangle, a->translation, a->dT, a->B, a->invert, a->d_axisangle,
                                            a->d_translation, st));

@@ -4,9 +4,28 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "tdl.h"
 
 namespace tdl {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: opt in once per device the
+// process launches on, not once per process (a second GPU would otherwise fail with cudaErrorInvalidValue).
+struct SmemOptIn {
+    std::atomic<unsigned long long> done{0};
+    template <typename Kernel>
+    cudaError_t operator()(Kernel kernel, size_t bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+        return e;
+    }
+};
 
 struct DepthParamsH {
     float min_disp, range;

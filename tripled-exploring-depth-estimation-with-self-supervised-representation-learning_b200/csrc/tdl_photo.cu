@@ -707,7 +707,8 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
     __shared__ float s_dP[TDL_MAX_SRC * 12];
     __shared__ int s_cnt[TDL_MAX_SRC];
-    __shared__ int s_nall;              // selected windows of the tile (all frames); later the live-pair counter
+    __shared__ int s_nall;              // selected windows of the tile (all frames)
+    __shared__ int s_nlive;             // sparse path: live (frame, pixel) pairs (its own counter: zeroed before the first barrier)
     __shared__ unsigned short s_list[PH * PW + 128];   // selected windows (<= PH*PW); sparse path: 128 windows + 9*128 live pairs
     __shared__ int s_tx0[kTW], s_tx1[kTW], s_ty0[kTH], s_ty1[kTH];
     __shared__ float s_tlx[kTW], s_tly[kTH];
@@ -737,6 +738,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     }
     if (tid >= 128 && tid < 128 + TDL_MAX_SRC) s_cnt[tid - 128] = 0;
     if (tid == 255) s_nall = 0;
+    if (tid == 254) s_nlive = 0;
     if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
     const float* s_iK = s_cam + TDL_MAX_SRC * 12;
     if (tid < kTW) up_index(tx0 + tid, p.sx[s], w, s_tx0[tid], s_tx1[tid], s_tlx[tid]);
@@ -890,8 +892,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
         unsigned* s_bits = reinterpret_cast<unsigned*>(s_coef + S * 3 * TP);   // [S][TP / 32]: pixel already in the live list
         for (int i = tid; i < S * 3 * TP; i += kNT) s_G[i] = 0.f;
         if (tid < S * TP / 32) s_bits[tid] = 0u;
-        __syncthreads();                                      // (everyone has read n_all: the counter can be reused)
-        if (tid == 0) s_nall = 0;
+        __syncthreads();
         unsigned short* s_live = s_list + 128;                // <= 9 * n_all <= 1152 entries, behind the <= 128 windows
         for (int e = tid; e < 3 * n_all; e += kNT) {          // one thread per (selected window, channel)
             const int ent = s_list[e / 3], ch = e - (e / 3) * 3;
@@ -916,7 +917,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
                         // the channel-0 thread of the window enters the pixel into the live list, once per (frame, pixel)
                         if (ch == 0 && tx0 + lx < W && ty0 + ly < H &&
                             !(atomicOr(&s_bits[f * (TP / 32) + (px >> 5)], 1u << (px & 31)) & (1u << (px & 31))))
-                            s_live[atomicAdd(&s_nall, 1)] = (unsigned short)(px | (f << 11));
+                            s_live[atomicAdd(&s_nlive, 1)] = (unsigned short)(px | (f << 11));
                     }
                 }
             }
@@ -927,7 +928,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
             }
         }
         __syncthreads();
-        const int n_act = s_nall;
+        const int n_act = s_nlive;
         float* dd = p.d_disp[s] + (size_t)b * h * w;
         for (int e0 = wrp * 32; e0 < n_act; e0 += kNT) {      // warp-uniform trip count: the dP reduction below is warp-wide
             const int e = e0 + lane;
@@ -1190,12 +1191,8 @@ template <int S>
 static cudaError_t launch_fwd_fused(const PhotoDev& p, cudaStream_t st) {
     constexpr int PLANE = (kTW + 2) * (kTH + 2);
     const size_t smem = (size_t)(3 + 3 * S) * PLANE * sizeof(float) + (size_t)6 * kR * kNT * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(photo_fwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    static SmemOptIn opt_in;
+    if (cudaError_t e = opt_in(photo_fwd_kernel<S>, smem)) return e;
     dim3 grid((p.W + kTW - 1) / kTW, (p.H + kTH - 1) / kTH, p.B);
     photo_fwd_kernel<S><<<grid, kNT, smem, st>>>(p);
     return cudaGetLastError();
@@ -1224,12 +1221,8 @@ static cudaError_t launch_score_t(const PhotoDev& p, cudaStream_t st) {
     PhotoMaps maps, wmaps;
     if (!encode_fwd_maps<S>(p, &maps, &wmaps)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)(1 + S + (S <= 2 ? S : 0)) * kFGROUP * sizeof(float) + (size_t)6 * kR * kNT * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(photo_score_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    static SmemOptIn opt_in;
+    if (cudaError_t e = opt_in(photo_score_kernel<S>, smem)) return e;
     dim3 grid((p.W + kTW - 1) / kTW, (p.H + kTH - 1) / kTH, p.B);
     photo_score_kernel<S><<<grid, kNT, smem, st>>>(p, maps, wmaps);
     return cudaGetLastError();
@@ -1267,12 +1260,8 @@ cudaError_t launch_photo_score(const PhotoDev& p, cudaStream_t st) {
 template <int S, bool kTMA>
 static cudaError_t launch_bwd_k(const PhotoDev& p, const PhotoMaps& maps, cudaStream_t st) {
     const size_t smem = (size_t)((1 + S) * kQGROUP + 9 * kQPLANE) * sizeof(float) + kQPLANE;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(photo_bwd_kernel<S, kTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    static SmemOptIn opt_in;
+    if (cudaError_t e = opt_in(photo_bwd_kernel<S, kTMA>, smem)) return e;
     dim3 grid((p.W + kTW - 1) / kTW, (p.H + kTH - 1) / kTH, p.B * p.nscales);
     photo_bwd_kernel<S, kTMA><<<grid, kNT, smem, st>>>(p, maps);
     return cudaGetLastError();
@@ -1473,12 +1462,8 @@ cudaError_t launch_recon_fwd(const ReconArgsDev& a, cudaStream_t st) {
     ReconDev p{a.B, a.h, a.w, a.coef, a.pred, a.tgt, a.mask, a.acc, a.loss, a.dloss, a.d_pred};
     constexpr int PLANE = (kTW + 2) * (kTH + 2);
     const size_t smem = (size_t)6 * PLANE * sizeof(float) + (size_t)6 * kR * kNT * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(recon_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    static SmemOptIn opt_in;
+    if (cudaError_t e = opt_in(recon_fwd_kernel, smem)) return e;
     dim3 grid((a.w + kTW - 1) / kTW, (a.h + kTH - 1) / kTH, a.B);
     recon_fwd_kernel<<<grid, kNT, smem, st>>>(p);
     cudaError_t e = cudaGetLastError();
@@ -1491,12 +1476,8 @@ cudaError_t launch_recon_bwd(const ReconArgsDev& a, cudaStream_t st) {
     ReconDev p{a.B, a.h, a.w, a.coef, a.pred, a.tgt, a.mask, a.acc, a.loss, a.dloss, a.d_pred};
     constexpr int QPLANE = (kTW + 4) * (kTH + 4);
     const size_t smem = (size_t)16 * QPLANE * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(recon_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    static SmemOptIn opt_in;
+    if (cudaError_t e = opt_in(recon_bwd_kernel, smem)) return e;
     dim3 grid((a.w + kTW - 1) / kTW, (a.h + kTH - 1) / kTH, a.B);
     recon_bwd_kernel<<<grid, kNT, smem, st>>>(p);
     return cudaGetLastError();

@@ -53,16 +53,14 @@ inline bool encode_image_map(CUtensorMap* map, const float* base, int planes, in
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const EncodeFn fn = [] {          // resolved once (thread-safe static initialisation)
         void* ptr = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeFn>(ptr);
-    }
+            return reinterpret_cast<EncodeFn>(ptr);
+        return static_cast<EncodeFn>(nullptr);
+    }();
     if (!fn) return false;
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (W & 3) != 0 || ((box_w * 4) & 15) != 0) return false;
     if (box_w > 256 || box_h > 256 || box_p > 256) return false;

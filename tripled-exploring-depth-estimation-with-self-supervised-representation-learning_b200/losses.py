@@ -36,25 +36,51 @@ from .ops import (EdgeAwareSmoothness, EdgeConfig, FeatConfig, FeatureMetricLoss
 
 
 class LossDict(dict):
-    """The reference's ``loss_dict`` (same keys, 0-dim tensors) plus ``total()``: the sum of all entries
-    -- what ``batch_processor`` computes (mono/apis/trainer.py:39-48) -- evaluated from the raw kernel
-    outputs with two tiny kernels instead of one add (and one autograd node) per entry."""
+    """The reference's ``loss_dict`` (same keys, 0-dim tensors) plus ``total()``: the sum of the ``.mean()`` of all
+    entries -- what ``batch_processor`` computes (mono/apis/trainer.py:39-48).  Entries that came out of one fused
+    kernel call are registered as a *part* (the raw kernel output vector, the keys it covers); ``total()`` sums each
+    part with one kernel and adds ``.mean()`` of every entry no part covers, so terms a subclass appends the
+    reference's way (``loss_dict[k] = v`` / ``loss_dict.update(...)``) are never dropped from the objective."""
 
     def __init__(self):
         super().__init__()
-        self._parts = []          # (tensor, multiplicity)
+        self._parts = []          # (tensor, multiplicity, keys covered)
 
-    def add_part(self, tensor, mult=1):
-        self._parts.append((tensor, mult))
+    def add_part(self, tensor, mult=1, keys=()):
+        self._parts.append((tensor, mult, tuple(keys)))
+
+    def absorb(self, other: "LossDict"):
+        """update() with another LossDict, keeping its parts."""
+        super().update(other)
+        self._parts += other._parts
+
+    def __setitem__(self, key, value):
+        # overwriting an entry a part stands in for drops that part: its other entries (views of the part's
+        # tensor) are then summed one by one, which is the same value
+        if key in self and self[key] is not value:
+            self._parts = [p for p in self._parts if key not in p[2]]
+        super().__setitem__(key, value)
+
+    def __delitem__(self, key):
+        self._parts = [p for p in self._parts if key not in p[2]]
+        super().__delitem__(key)
+
+    def update(self, *a, **kw):
+        for k, v in dict(*a, **kw).items():
+            self[k] = v
 
     def total(self):
-        if not self._parts:
-            return sum(self.values())
         out = None
-        for t, m in self._parts:
+        covered = set()
+        for t, m, keys in self._parts:
             v = t.sum() if t.dim() else t
             v = v * m if m != 1 else v
             out = v if out is None else out + v
+            covered.update(keys)
+        for k, v in self.items():
+            if k not in covered:
+                v = v.mean() if v.dim() else v
+                out = v if out is None else out + v
         return out
 
 
@@ -71,7 +97,6 @@ class ViewSynthesisLossMixin:
     materialize_outputs = True          # write outputs[("color",f,s)] / ("feature",f,0) / ("min_index",s)
     grid_sample_align_corners = False   # torch >= 1.3 default, which is what the reference runs with today
     _smooth_weight_key = "smoothness_weight"
-    _noise_calls = 0
     overlap_streams = True              # feature-metric kernels on a second stream (see compute_losses_fm)
     _streams = {}
 
@@ -106,7 +131,10 @@ class ViewSynthesisLossMixin:
         if noise is None and opt.automask and self.noise_mode == "reference":
             noise = self._reference_noise(scales, target.shape[0], target.device)
         sw = _opt_get(opt, self._smooth_weight_key, 0.0)
-        type(self)._noise_calls += 1
+        # Philox stream: (torch.initial_seed(), per-instance step counter) -- reproducible per model instance after
+        # torch.manual_seed, independent of how many other loss objects live in the process
+        step = self.__dict__.get("_tdl_noise_step", 0) + 1
+        self.__dict__["_tdl_noise_step"] = step
         cfg = PhotoConfig(
             n_src=len(frames), n_scales=len(scales),
             min_depth=float(opt.min_depth), max_depth=float(opt.max_depth),
@@ -115,7 +143,7 @@ class ViewSynthesisLossMixin:
             photo_coef=tuple(1.0 / n for _ in scales),
             smooth_coef=tuple(sw / (2 ** s) / n for s in scales),
             materialize=self.materialize_outputs if materialize is None else materialize,
-            noise_seed=(torch.initial_seed() * 1000003 + type(self)._noise_calls) & (2 ** 63 - 1),
+            noise_seed=(torch.initial_seed() * 1000003 + step) & (2 ** 63 - 1),
             has_noise=noise is not None and bool(opt.automask))
         P = self._stack_P(inputs, outputs, inputs["K"])
         invK = inputs["inv_K"][:, :3, :3]
@@ -180,10 +208,10 @@ class ViewSynthesisLossMixin:
         scales = list(self.opt.scales)
         losses = self._photometric(inputs, outputs, scales, noise)
         loss_dict = LossDict()
-        loss_dict.add_part(losses)
         for i, s in enumerate(scales):
             loss_dict[("min_reconstruct_loss", s)] = losses[i]
             loss_dict[("smooth_loss", s)] = losses[len(scales) + i]
+        loss_dict.add_part(losses, 1, [("min_reconstruct_loss", s) for s in scales] + [("smooth_loss", s) for s in scales])
         return loss_dict
 
     def compute_losses_fm(self, inputs, outputs, noise=None, tgt_f=None, src_fs=None):
@@ -207,16 +235,22 @@ class ViewSynthesisLossMixin:
                 per, idx = self._feature_metric(inputs, outputs, tgt_f, src_fs, opt.perception_weight / len(scales))
             loss_dict = self.compute_losses_baseline(inputs, outputs, noise)
             main.wait_stream(side)
+            # allocated while `side` was current but consumed on `main`: tell the caching allocator, so the blocks are
+            # not handed to the next side-stream kernel while main-stream readers are still queued
+            for t in [per, idx] + [outputs.get(("feature", f, 0)) for f in self._src_frames()]:
+                if t is not None:
+                    t.record_stream(main)
         else:
             loss_dict = self.compute_losses_baseline(inputs, outputs, noise)
             per, idx = self._feature_metric(inputs, outputs, tgt_f, src_fs, opt.perception_weight / len(scales))
         ordered = LossDict()
-        ordered._parts = list(loss_dict._parts)
-        ordered.add_part(per, len(scales))
         for s in scales:
             ordered[("min_reconstruct_loss", s)] = loss_dict[("min_reconstruct_loss", s)]
             ordered[("min_perceptional_loss", s)] = per
             ordered[("smooth_loss", s)] = loss_dict[("smooth_loss", s)]
+        ordered._parts = list(loss_dict._parts)
+        ordered.add_part(per, len(scales), [("min_perceptional_loss", s) for s in scales])
+        for s in scales:
             if idx is not None:
                 outputs[("min_index", s)] = idx        # the reference overwrites it (net.py:117)
         return ordered
@@ -232,12 +266,10 @@ class ViewSynthesisLossMixin:
             for i in range(5):
                 loss_dict[("feature_regularization_loss", i)] = self.get_feature_regularization_loss(
                     features[i], target) / (2 ** i) / 5
-                loss_dict.add_part(loss_dict[("feature_regularization_loss", i)])
             if src_fs is None:
                 src_fs = {f: self._extract(inputs[("color", f, 0)]) for f in self._src_frames()}
             per, idx = self._feature_metric(inputs, outputs, features[0], src_fs, opt.perception_weight)
             loss_dict["min_perceptional_loss"] = per
-            loss_dict.add_part(per)
             if idx is not None:
                 outputs["min_index"] = idx
         w_rec = _opt_get(opt, "img_reconstruct_weight", 1)
@@ -250,10 +282,8 @@ class ViewSynthesisLossMixin:
                 msk_r = F.interpolate(mask, size, mode="bilinear", align_corners=False)
                 rec = MaskedReconstructionLoss.apply(float(w_rec) / len(opt.scales), res, tgt_r, msk_r)[0]
                 loss_dict[("img_reconstruct_loss", s)] = rec
-                loss_dict.add_part(rec)
         base = self.compute_losses_baseline(inputs, outputs, noise)
-        loss_dict.update(base)
-        loss_dict._parts += base._parts
+        loss_dict.absorb(base)
         return loss_dict
 
     def compute_auto_res_loss(self, inputs, outputs):

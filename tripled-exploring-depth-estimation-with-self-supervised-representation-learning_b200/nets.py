@@ -122,7 +122,5 @@ class mono_fm_joint_inpaint_disentangle(mono_fm_joint_inpaint):
 
     def compute_losses(self, inputs, outputs, features):
         loss_dict = super().compute_losses(inputs, outputs, features)
-        for k, v in self.compute_auto_res_loss(inputs, outputs).items():
-            loss_dict[k] = v
-            loss_dict.add_part(v.mean())
+        loss_dict.update(self.compute_auto_res_loss(inputs, outputs))     # as the reference does (net.py:530)
         return loss_dict
