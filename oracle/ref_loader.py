@@ -1,10 +1,11 @@
 """Import the *real* reference loss classes from ``/root/reference``.
 
 TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  ``/root/reference``
-exists only in the build container, so everything that needs it is gated on
-``reference_available()``: the CPU test ``tests/test_oracle_vs_reference.py``
-(pins ``oracle.restatement`` bit-for-bit against the reference) and
-``tests/golden/make_golden.py`` (writes the committed golden vectors).
+exists only in the build container; ``oracle/make_ref.py`` places the unmodified loss
+modules under the git-ignored ``oracle/_ref/`` so that they also reach the GPU box.
+Everything that needs them is gated on ``reference_available()``: ``tests/test_oracle_vs_reference.py``
+(pins ``oracle.restatement`` bit-for-bit against the reference), ``tests/golden/make_golden.py``
+(writes the committed golden vectors) and the ``--impl reference`` / ``cpu_baseline`` legs of ``bench.py``.
 
 The reference does not import as shipped (SURVEY.md "five facts" 3 and 4), so
 the loader
@@ -29,11 +30,28 @@ import types
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("TDL_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """The build container has the reference checkout; the GPU box only has ``oracle/_ref`` (the unmodified loss
+    modules placed there by ``oracle/make_ref.py``, git-ignored, checked against their SHA-256 manifest)."""
+    env = os.environ.get("TDL_REFERENCE_ROOT", "/root/reference")
+    if os.path.isfile(os.path.join(env, "mono", "model", "mono_fm", "net.py")):
+        return env, "checkout"
+    ref = os.path.join(_HERE, "_ref")
+    if os.path.isfile(os.path.join(ref, "mono", "model", "mono_fm", "net.py")):
+        from . import make_ref
+        if make_ref.verify(ref):
+            return ref, "oracle/_ref"
+    return env, None
+
+
+REF_ROOT, REF_KIND = _find_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "mono", "model", "mono_fm", "net.py"))
+    return REF_KIND is not None
 
 
 def _stub(name, path=None, **attrs):
@@ -125,6 +143,7 @@ def make_loss_only_net(kind, opt):
 
     kind: 'baseline' (mono/model/mono_baseline/net.py:51-100),
           'fm'       (mono/model/mono_fm/net.py:69-133),
+          'joint'    (mono/model/mono_fm_joint/net.py:73-155),
           'inpaint'  (mono/model/mono_fm_joint_inpaint/net.py:47-133),
           'tripled'  (mono/model/mono_fm_joint_inpaint/net.py:398-532, adds auto_res_loss).
     """
@@ -136,6 +155,8 @@ def make_loss_only_net(kind, opt):
         cls = mods["fm"].mono_fm
     elif kind == "inpaint":
         cls = mods["inpaint"].mono_fm_joint_inpaint
+    elif kind == "joint":                        # mono/model/mono_fm_joint/net.py:73-155
+        cls = mods["joint"].mono_fm_joint
     elif kind == "tripled":                      # the TripleD net of config/cfg_kitti_tripleD.py
         cls = mods["inpaint"].mono_fm_joint_inpaint_disentangle
     else:
@@ -150,6 +171,22 @@ def make_loss_only_net(kind, opt):
     net.project_3d = proj
     if kind == "fm":
         net.extractor = _Feat()
-    if kind in ("inpaint", "tripled"):
+    if kind in ("inpaint", "tripled", "joint"):
         net.Encoder = _Feat()
     return net
+
+
+def run_reference_loss(kind, opt, inputs, outputs, tgt_feat=None, src_feats=None, features=None):
+    """Executes the reference's own ``compute_losses`` (the class named by ``kind``, see make_loss_only_net) on the
+    given tensors -> loss_dict.  ``outputs`` is updated in place like the reference does (warped images, min_index).
+    Feature maps stand in for the extractor's output through the data_ptr table of ``_Feat``."""
+    net = make_loss_only_net(kind, opt)
+    if tgt_feat is not None:
+        table = {inputs[("color", 0, 0)].data_ptr(): tgt_feat}
+        for f, t in src_feats.items():
+            table[inputs[("color", f, 0)].data_ptr()] = t
+        (net.extractor if kind == "fm" else net.Encoder).table = table
+    with cpu_cuda_shim():
+        if kind in ("inpaint", "tripled", "joint"):
+            return net.compute_losses(inputs, outputs, features)
+        return net.compute_losses(inputs, outputs)

@@ -4,8 +4,9 @@ TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Everything here runs on
 the CPU in fp32 (or fp64 for finite-difference style checks) with stock torch
 ops, in the same operation order as the reference, so that on the same seeded
 inputs it is bit-identical to the reference executed by the same torch build
-(``tests/test_oracle_vs_reference.py`` checks that whenever ``/root/reference``
-is present; ``tests/golden/*.pt`` pins it everywhere else).
+(``tests/test_oracle_vs_reference.py`` checks that whenever the reference is reachable --
+``/root/reference`` in the build container, ``oracle/_ref`` on the GPU box; ``tests/golden/*.pt``
+pins it everywhere else).
 
 File:line citations are relative to ``/root/reference``.
 
@@ -303,6 +304,34 @@ def compute_losses_inpaint_core(spec: LossSpec, inputs, outputs, noise, tgt_feat
         loss[("min_reconstruct_loss", s)], outputs[("min_index", s)] = \
             photometric_scale(spec, inputs, outputs, s, noise, forced.get(("photo", s)))
         outputs[("min_index_photo", s)] = outputs[("min_index", s)]
+        loss[("smooth_loss", s)] = smooth_scale(spec, inputs, outputs, s, spec.smoothness_weight)
+    return loss
+
+
+def compute_losses_joint(spec: LossSpec, inputs, outputs, noise, features, src_feats, inv_K_half=None, forced=None):
+    """mono/model/mono_fm_joint/net.py:73-155: feature regularisation on the five encoder levels (:77-80), per scale the
+    UN-masked autoencoder reconstruction term (:96-101), photometric + automask min (:103-131), the feature-metric
+    term re-evaluated per scale like mono_fm (:133-143) and the smoothness term (:145-153)."""
+    loss = {}
+    forced = forced or {}
+    target = inputs[("color", 0, 0)]
+    for i in range(5):
+        loss[("feature_regularization_loss", i)] = feature_regularization_loss(
+            features[i], target, spec.extra["dis"], spec.extra["cvt"]) / (2 ** i) / 5
+    for s in spec.scales:
+        res_img = outputs[("res_img", 0, s)]
+        _, _, h, w = res_img.size()
+        target_resize = F.interpolate(target, [h, w], mode="bilinear", align_corners=False)
+        loss[("img_reconstruct_loss", s)] = reprojection_loss(res_img, target_resize).mean() / len(spec.scales)
+        images_pred(spec, inputs, outputs, s)
+        features_pred(spec, inputs, outputs, src_feats, inv_K_half)
+        loss[("min_reconstruct_loss", s)], outputs[("min_index_photo", s)] = \
+            photometric_scale(spec, inputs, outputs, s, noise, forced.get(("photo", s)))
+        per = torch.cat([perceptional_loss(features[0], outputs[("feature", f, 0)])
+                         for f in spec.frame_ids[1:]], 1)
+        outputs["feat_stack"] = per.detach()
+        m, outputs[("min_index", s)] = _select_min(per, forced.get("feat"))
+        loss[("min_perceptional_loss", s)] = spec.perception_weight * m.mean() / len(spec.scales)
         loss[("smooth_loss", s)] = smooth_scale(spec, inputs, outputs, s, spec.smoothness_weight)
     return loss
 

@@ -13,6 +13,7 @@ PKG_NAME = "tripled-exploring-depth-estimation-with-self-supervised-representati
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: oracle comparison at a benchmarked configuration (seconds of CPU oracle time)")
 
 
 @pytest.fixture(scope="session")

@@ -27,6 +27,8 @@ CASES = {
     "baseline_waves_b2_64x96": ("baseline", 2, 64, 96, "waves", 0, 1234),
     "fm_waves_b2_64x96_c8": ("fm", 2, 64, 96, "waves", 8, 1236),
     "inpaint_waves_b1_96x128_c8": ("inpaint", 1, 96, 128, "waves", 8, 1237),
+    # mono_fm_joint (mono/model/mono_fm_joint/net.py:73-155): per-scale perceptual keys, UN-masked reconstruction
+    "joint_waves_b1_96x128_c8": ("joint", 1, 96, 128, "waves", 8, 1240),
     # TripleD net (cfg_kitti_tripleD): + masked autoencoder reconstruction (16 erased 8x8 holes) + auto_res_loss
     "tripled_waves_b1_96x128_c8": ("tripled", 1, 96, 128, "waves", 8, 1238),
     # "smooth": box-filtered noise frames -- realistic, judged with the kink-robust metric
@@ -58,7 +60,7 @@ def run_reference(kind, B, H, W, frames, C, seed):
             table[inputs[("color", f, 0)].data_ptr()] = t
         table[inputs[("color", 0, 0)].data_ptr()] = tgt
         (net.extractor if kind == "fm" else net.Encoder).table = table
-        if kind in ("inpaint", "tripled"):
+        if kind in ("inpaint", "tripled", "joint"):
             # 5 feature levels; only level 0 enters the view-synthesis path, the
             # others feed get_feature_regularization_loss.
             g = torch.Generator().manual_seed(seed + 99)
@@ -73,18 +75,20 @@ def run_reference(kind, B, H, W, frames, C, seed):
                     y0 = int(torch.randint(0, H - 8, (1,), generator=g))
                     x0 = int(torch.randint(0, W - 8, (1,), generator=g))
                     mask[:, :, y0:y0 + 8, x0:x0 + 8] = 0
+            if kind in ("tripled", "joint"):
                 for s in range(4):
                     r = torch.sigmoid(torch.nn.functional.avg_pool2d(
                         torch.randn(B, 3, (H >> s) + 4, (W >> s) + 4, generator=g), 5, 1) * 2).requires_grad_(True)
                     leaves[("res_img", 0, s)] = r
                     outputs[("res_img", 0, s)] = r
+            if kind == "tripled":
                 a = (inputs[("color", 0, 0)] + 0.05 * torch.randn(B, 3, H, W, generator=g)).clamp(0, 1).requires_grad_(True)
                 leaves[("auto_res_img", 0, 0)] = a
                 outputs[("auto_res_img", 0, 0)] = a
             inputs[("mask", 0, 0)] = mask
     torch.manual_seed(seed)          # the reference draws automask noise from the global CPU RNG
     with ref_loader.cpu_cuda_shim():
-        if kind in ("inpaint", "tripled"):
+        if kind in ("inpaint", "tripled", "joint"):
             loss_dict = net.compute_losses(inputs, outputs, features)
         else:
             loss_dict = net.compute_losses(inputs, outputs)
@@ -105,7 +109,10 @@ def run_reference(kind, B, H, W, frames, C, seed):
 
 
 def main():
+    only = sys.argv[1:]
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         rec = run_reference(*case)
         path = os.path.join(HERE, name + ".pt")
         torch.save(rec, path)

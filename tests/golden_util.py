@@ -47,6 +47,9 @@ def run_restatement(rec, dtype=torch.float32, forced=None):
         src = {f: leaves[("src_feat", f)] for f in spec.frame_ids[1:]}
         if kind == "fm":
             loss = R.compute_losses_fm(spec, inputs, outputs, noise, leaves["tgt_feat"], src, forced=forced)
+        elif kind == "joint":
+            feats = [leaves["tgt_feat"]] + [leaves[("feat_level", i)] for i in range(1, 5)]
+            loss = R.compute_losses_joint(spec, inputs, outputs, noise, feats, src, forced=forced)
         else:
             loss = {}
             feats = [leaves["tgt_feat"]] + [leaves[("feat_level", i)] for i in range(1, 5)]

@@ -46,6 +46,9 @@ def run_cuda(rec, noise, dev="cuda", kind=None):
         src = {f: leaves[("src_feat", f)] for f in frames}
         if kind == "fm":
             loss = net.compute_losses_fm(inputs, outputs, noise_d, leaves["tgt_feat"], src)
+        elif kind == "joint":
+            feats = [leaves["tgt_feat"]] + [leaves[("feat_level", i)] for i in range(1, 5)]
+            loss = net.compute_losses_joint(inputs, outputs, feats, noise_d, src)
         else:
             feats = [leaves["tgt_feat"]] + [leaves[("feat_level", i)] for i in range(1, 5)]
             loss = net.compute_losses_joint_core(inputs, outputs, feats, noise_d, src)

@@ -35,6 +35,8 @@ def _inputs(tdl, B=2):
 @pytest.mark.parametrize("name,keys", [
     ("Baseline", [("min_reconstruct_loss", 0), ("smooth_loss", 3)]),
     ("mono_fm", [("min_reconstruct_loss", 0), ("min_perceptional_loss", 2), ("smooth_loss", 3)]),
+    ("mono_fm_joint", [("feature_regularization_loss", 4), ("min_perceptional_loss", 3), ("img_reconstruct_loss", 1),
+                       ("min_reconstruct_loss", 0), ("smooth_loss", 2)]),
     ("mono_fm_joint_inpaint_disentangle", [("feature_regularization_loss", 4), "min_perceptional_loss",
                                            ("img_reconstruct_loss", 1), ("min_reconstruct_loss", 0), "auto_res_loss"]),
 ])

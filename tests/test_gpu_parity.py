@@ -14,10 +14,13 @@ one-sided derivative a pixel gets (the reference run on another device flips the
   * |.| in the smoothness term: sign(second difference) where that difference is ~1e-8;
   * torch.clamp(SSIM, 0, 1) and the arg-min itself (next paragraph).
 Each event changes the gradient of ONE pixel by O(1) of that pixel's own gradient.  Gradients are
-therefore judged with a kink-robust metric: relative L2 after discarding the K largest-error elements
-(K = max(16, 4e-3 * numel), at most 2 % of the tensor) must meet the 1e-4 tolerance, the untrimmed
-error is bounded by 2e-2, and the pose gradients -- sums over all pixels, so events cannot be
-separated -- by 1e-3 (3e-4 on the band-limited "waves" frames, where interpolation kinks are tiny).
+therefore judged in two regimes (both numbers are always printed and collected in profiles/parity_r2.md):
+  * band-limited "waves" fixtures (no interpolation kinks to speak of): the UNTRIMMED relative L2 of every gradient --
+    disparity, pose and features -- must meet the 1e-4 tolerance of north_star as it stands;
+  * "smooth" / "white" / "scene" frames (textured: every integer crossing of a source coordinate is a kink): relative L2
+    after discarding the K largest-error elements (K = max(16, 4e-3 * numel), at most 2 % of the tensor) must meet
+    1e-4, the untrimmed error is bounded by 2e-2, and the pose gradients -- sums over all pixels, so events cannot be
+    separated -- by 1e-3.
 
 Arg-min near-ties.  min-reprojection is a hard select, so a 1e-8 difference in an SSIM value
 can move the arg-min of a pixel whose two best channels are (almost) equal, and with it that
@@ -27,6 +30,9 @@ pixel's whole gradient -- the reference on another device does the same.  The te
   * when there is such a flip, compare gradients against the oracle evaluated with OUR
     selection imposed (same backward rule: gradient to the selected channel only).
 """
+import json
+import os
+
 import pytest
 import torch
 
@@ -59,9 +65,13 @@ def _trimmed_rel_l2(a, b, k):
     return float(e2.sum().sqrt() / b.double().norm().clamp_min(1e-30))
 
 
+REPORT = os.environ.get("TDL_PARITY_REPORT")      # JSON lines, one per checked case (tests/parity_report.py formats them)
+
+
 def _check(rec, tag, golden=None, img_rtol=IMG_RTOL, grad_rtol=GRAD_RTOL, flip_budget=FLIP_BUDGET):
     meta = rec["meta"]
-    pose_rtol = (3 if meta["frames"] == "waves" else 10) * grad_rtol
+    strict = meta["frames"] == "waves"            # untrimmed 1e-4 on every gradient
+    pose_rtol = (1 if strict else 10) * grad_rtol
     # one fp32 evaluation of SSIM on smooth content carries ~1e-5 of absolute noise per pixel (see TIE_ATOL);
     # the loss is its mean, so the scalar is only defined to ~1e-5/sqrt(N)/loss: 1e-5 relative holds from
     # BASELINE-sized inputs (>= 192x640) down to ~50k pixels, the tiny fixtures get 3e-5
@@ -74,7 +84,7 @@ def _check(rec, tag, golden=None, img_rtol=IMG_RTOL, grad_rtol=GRAD_RTOL, flip_b
     # ---- arg-min maps: flips must be near-ties
     forced, flips_total = {}, 0
     for k, ours in outs.items():
-        if k == "min_index" or (isinstance(k, tuple) and k[0] == "min_index" and meta["kind"] == "fm"):
+        if k == "min_index" or (isinstance(k, tuple) and k[0] == "min_index" and meta["kind"] in ("fm", "joint")):
             stack, fkey, okey = ref_out["feat_stack"], "feat", k
         elif isinstance(k, tuple) and k[0] == "min_index_photo":
             stack, fkey, okey = ref_out[("reproj_stack", k[1])], ("photo", k[1]), k
@@ -124,8 +134,9 @@ def _check(rec, tag, golden=None, img_rtol=IMG_RTOL, grad_rtol=GRAD_RTOL, flip_b
             n_trim = min(max(16, g.numel() // 250), g.numel() // 50)
             trimmed = _trimmed_rel_l2(grads[k], g, n_trim)
             report[f"grad {k} trimmed"] = trimmed
-            assert trimmed <= grad_rtol and err <= 200 * grad_rtol, \
-                f"{tag} grad {k}: rel-L2 {err:.3e}, without the {n_trim} largest-error cells {trimmed:.3e}"
+            lim = grad_rtol if strict else 200 * grad_rtol
+            assert trimmed <= grad_rtol and err <= lim, \
+                f"{tag} grad {k}: rel-L2 {err:.3e} (limit {lim:.0e}), without the {n_trim} largest-error cells {trimmed:.3e}"
 
     # ---- the golden vectors themselves (produced by the real reference)
     if golden is not None:
@@ -143,6 +154,11 @@ def _check(rec, tag, golden=None, img_rtol=IMG_RTOL, grad_rtol=GRAD_RTOL, flip_b
                     assert _trimmed_rel_l2(grads[k], g, 0 if lim == pose_rtol else n_trim) <= lim, \
                         f"{tag} golden grad {k}"
     print(tag, {k: (f"{v:.1e}" if isinstance(v, float) else v) for k, v in report.items()})
+    if REPORT:
+        with open(REPORT, "a") as fh:
+            fh.write(json.dumps({"case": tag, "frames": meta["frames"], "kind": meta["kind"], "strict": strict,
+                                 "shape": [meta["B"], meta["H"], meta["W"], meta.get("C", 0)],
+                                 "report": {str(k): v for k, v in report.items()}}) + "\n")
     return report
 
 
@@ -156,18 +172,40 @@ def test_cuda_matches_reference_golden(name):
         _check(rec, name, golden=rec)
 
 
-def _synthetic_record(kind, B, H, W, C, seed, frames="smooth", frame_ids=(0, -1, 1)):
+def _synthetic_record(kind, B, H, W, C, seed, frames="smooth", frame_ids=(0, -1, 1), level_widths=(4, 4, 4, 4), hole=8):
+    """kind: baseline | fm | joint | inpaint | tripled.  The joint / TripleD kinds add the five encoder levels (level 0 =
+    the C-channel feature map of the view-synthesis term, levels 1-4 with `level_widths` channels at H/4 .. H/32), the
+    autoencoder outputs ("res_img", 0, s), and for TripleD the erase mask (16 holes of `hole` x `hole` pixels,
+    cfg_kitti_tripleD.py:19-20) and ("auto_res_img", 0, 0)."""
     tdl = pkg()
     inputs, outputs, extras = tdl.synth.make_inputs(B, H, W, frame_ids=frame_ids, seed=seed, frames=frames,
                                                     feat_channels=C, with_noise=False)
     opt = dict(frame_ids=list(frame_ids), imgs_per_gpu=B, height=H, width=W, scales=[0, 1, 2, 3],
                min_depth=0.1, max_depth=100.0, automask=True, disp_norm=True, perception_weight=1e-3,
-               smoothness_weight=1e-3, disparity_smoothness=1e-3, dis=1e-3, cvt=1e-3)
+               smoothness_weight=1e-3, disparity_smoothness=1e-3, dis=1e-3, cvt=1e-3,
+               img_reconstruct_weight=1 if kind == "tripled" else 0, auto_res_weight=5e-3)
     leaves = dict(outputs)
     if C:
         leaves["tgt_feat"] = extras["tgt_feat"]
         for f, t in extras["src_feats"].items():
             leaves[("src_feat", f)] = t
+    if kind in ("joint", "inpaint", "tripled"):
+        g = torch.Generator().manual_seed(seed + 99)
+        for i, cw in zip(range(1, 5), level_widths):
+            leaves[("feat_level", i)] = torch.randn(B, cw, H >> (i + 1), W >> (i + 1), generator=g)
+        mask = torch.ones(B, 3, H, W)
+        if kind == "tripled":
+            for _ in range(16):
+                y0 = int(torch.randint(0, H - hole, (1,), generator=g))
+                x0 = int(torch.randint(0, W - hole, (1,), generator=g))
+                mask[:, :, y0:y0 + hole, x0:x0 + hole] = 0
+        inputs[("mask", 0, 0)] = mask
+        if kind in ("joint", "tripled"):
+            for s in range(4):
+                leaves[("res_img", 0, s)] = torch.sigmoid(torch.nn.functional.avg_pool2d(
+                    torch.randn(B, 3, (H >> s) + 4, (W >> s) + 4, generator=g), 5, 1) * 2)
+        if kind == "tripled":
+            leaves[("auto_res_img", 0, 0)] = (inputs[("color", 0, 0)] + 0.05 * torch.randn(B, 3, H, W, generator=g)).clamp(0, 1)
     return {"inputs": inputs, "leaves": leaves,
             "meta": dict(kind=kind, B=B, H=H, W=W, frames=frames, C=C, seed=seed, opt=opt)}
 
@@ -182,6 +220,9 @@ def _synthetic_record(kind, B, H, W, C, seed, frames="smooth", frame_ids=(0, -1,
     ("baseline", 1, 96, 320, 0, 1236, (0, -2, -1, 1, 2), "smooth"),
     ("baseline", 1, 48, 80, 0, 1237, (0, 1), "waves"),              # partial tiles: 48, 80 are not multiples of 32
     ("baseline", 1, 64, 96, 0, 1239, (0, -1, 1), "white"),          # white-noise stress case
+    ("baseline", 2, 64, 96, 0, 1241, (0, "s"), "waves"),             # stereo pair: inputs["stereo_T"] (mono_fm/net.py:162-165)
+    ("fm", 1, 64, 96, 8, 1242, (0, -1, 1, "s"), "waves"),            # temporal + stereo sources (mono_dataset.py:194-199)
+    ("joint", 1, 96, 128, 8, 1243, (0, -1, 1), "smooth"),            # mono_fm_joint.compute_losses (mono_fm_joint/net.py:73-155)
 ])
 def test_cuda_matches_cpu_oracle(kind, B, H, W, C, seed, fids, frames):
     rec = _synthetic_record(kind, B, H, W, C, seed, frames=frames, frame_ids=fids)

@@ -255,6 +255,37 @@ class ViewSynthesisLossMixin:
                 outputs[("min_index", s)] = idx        # the reference overwrites it (net.py:117)
         return ordered
 
+    def compute_losses_joint(self, inputs, outputs, features, noise=None, src_fs=None):
+        """mono/model/mono_fm_joint/net.py:73-155 (the ``mono_fm_joint`` net): feature regularisation on the five encoder
+        levels (:77-80); per scale the UN-masked autoencoder reconstruction term SSIM + L1 of ``("res_img", 0, s)``
+        against the bilinearly resized target (:96-101), the photometric min-reprojection term (:103-131), the
+        feature-metric term under per-scale keys (:133-143; scale independent, evaluated once like compute_losses_fm)
+        and the smoothness term (:145-153)."""
+        opt = self.opt
+        scales = list(opt.scales)
+        n = len(scales)
+        target = inputs[("color", 0, 0)]
+        loss_dict = LossDict()
+        for i in range(5):
+            loss_dict[("feature_regularization_loss", i)] = self.get_feature_regularization_loss(
+                features[i], target) / (2 ** i) / 5
+        if src_fs is None:
+            src_fs = {f: self._extract(inputs[("color", f, 0)]) for f in self._src_frames()}
+        per, idx = self._feature_metric(inputs, outputs, features[0], src_fs, opt.perception_weight / n)
+        base = self.compute_losses_baseline(inputs, outputs, noise)
+        for s in scales:
+            res = outputs[("res_img", 0, s)]
+            tgt_r = F.interpolate(target, list(res.shape[-2:]), mode="bilinear", align_corners=False)
+            loss_dict[("img_reconstruct_loss", s)] = MaskedReconstructionLoss.apply(1.0 / n, res, tgt_r, None)[0]
+            loss_dict[("min_reconstruct_loss", s)] = base[("min_reconstruct_loss", s)]
+            loss_dict[("min_perceptional_loss", s)] = per
+            loss_dict[("smooth_loss", s)] = base[("smooth_loss", s)]
+            if idx is not None:
+                outputs[("min_index", s)] = idx        # the reference overwrites the photometric map (net.py:142)
+        loss_dict._parts = list(base._parts)
+        loss_dict.add_part(per, n, [("min_perceptional_loss", s) for s in scales])
+        return loss_dict
+
     def compute_losses_joint_core(self, inputs, outputs, features, noise=None, src_fs=None):
         """View-synthesis part of mono/model/mono_fm_joint_inpaint/net.py:47-133: one un-divided
         feature-metric term on features[0] (:58-70) and the per-scale photometric / smoothness terms

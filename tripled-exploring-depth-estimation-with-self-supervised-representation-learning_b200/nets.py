@@ -77,6 +77,29 @@ class mono_fm(_DepthPoseNet):
 
 
 @MONO.register_module
+class mono_fm_joint(_DepthPoseNet):
+    """Joint depth + autoencoder net (mono/model/mono_fm_joint/net.py:17-155): the feature encoder is trained in the
+    loop on the un-erased target, its decoder reconstructs the image at four scales (no erase mask)."""
+
+    def __init__(self, options):
+        super().__init__(options)
+        self.Encoder = ResnetEncoder(self.opt.get("extractor_num_layers", 50))
+        self.Decoder = ImageDecoder(self.Encoder.num_ch_enc, "res_img")
+
+    def forward(self, inputs):                     # net.py:47-58
+        outputs = self.DepthDecoder(self.DepthEncoder(inputs["color_aug", 0, 0]))
+        if not self.training:
+            return outputs
+        outputs.update(self.predict_poses(inputs))
+        features = self.Encoder(inputs[("color", 0, 0)])
+        outputs.update(self.Decoder(features, 0))
+        return outputs, self.compute_losses(inputs, outputs, features)
+
+    def compute_losses(self, inputs, outputs, features):
+        return self.compute_losses_joint(inputs, outputs, features)
+
+
+@MONO.register_module
 class mono_fm_joint_inpaint(_DepthPoseNet):
     """Joint depth + in-painting autoencoder net (mono/model/mono_fm_joint_inpaint/net.py:19-133): the feature
     encoder is trained in the loop on the erased target, its decoder reconstructs the image at four scales."""
