@@ -8,15 +8,25 @@ Workload (BASELINE.json configs[1], cfg_kitti_fm): the mono_fm loss -- 4-scale p
 (H/2, W/2) + edge-aware smoothness -- at 192x640, batch 8 per GPU, fp32, forward + backward,
 on synthetic frames (package synth.py).  One "step" = one fwd+bwd pass over one batch.
 
+Two synthetic workloads of that shape are measured (package synth.py):
+  "smooth"  SURVEY.md 8(d)'s recipe (BASELINE's): globally shifted sources + pixel-level random disparity.  The un-warped
+            sources win ~99 % of the arg-mins, i.e. a fully auto-masked scene: sparse photometric backward, scattered gathers.
+  "scene"   a moving camera in a smooth 3-D scene, sources rendered through ground-truth depth + pose, prediction = truth +
+            2 % error: the warped sources win ~92 % of the pixels (dense backward), the flow is coherent.  This is the
+            regime of a real training step, so `roofline` names the dominant kernel of THIS workload.
+
 Printed JSON line (rank 0):
-  value      images/s with every input already resident in HBM (CUDA-graph replay of the step)
-  e2e        images/s through the public host API with HOST (pinned) buffers: H2D of every input
-             of the step, the step, D2H of the loss scalars -- inside the timed region
-  roofline   dominant kernel: algorithmic bytes per launch / CUDA-event duration vs MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (oracle/restatement.py, a port of the reference's loss code) timed on
-             this box's host cores on a bounded sample (B=2) of the same workload
-With --impl reference the reference arm is timed instead: the reference's loss code path on the
-host cores (the oracle port; /root/reference does not exist on the GPU box).
+  value      images/s on "smooth" with every input already resident in HBM (CUDA-graph replay of the step): the
+             MEDIAN of `repeats.n` timed regions of exactly --steps replays each (min / max / all regions in `repeats`)
+  scene      the same measurement on "scene": images/s, ms/step, per-kernel table, identity_frac
+  e2e        images/s through the public host API with HOST (pinned) buffers: H2D of every input of the step, the step,
+             D2H of the loss scalars -- inside the timed region; e2e_images_only: only what a data loader provides is
+             uploaded (uint8 frames, K, inv_K), features come from a conv stem on the device
+  roofline   dominant kernel of "scene": algorithmic bytes per launch / CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline  the reference's own loss code (oracle/_ref, the unmodified reference modules; else the oracle port) timed
+             on this box's host cores on a bounded sample (B=2) of the same workload
+With --impl reference the reference arm is timed instead: the reference's mono_fm.compute_losses + backward on the host
+cores at the SAME batch, steps and warm-up as asked for (kind "reference" when oracle/_ref travelled, else "port").
 """
 from __future__ import annotations
 
@@ -61,7 +71,11 @@ def parse():
     ap.add_argument("--syncbn", action="store_true",
                     help="convert to SyncBatchNorm like cfg_kitti_fm (syncbn = True); off by default: its ~200 tiny "
                          "collectives per step halve 2-GPU throughput (measured: 186 vs 394 images/s)")
-    ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample of the cpu_baseline leg")
+    ap.add_argument("--repeats", type=int, default=7, help="timed regions of --steps replays each (median is reported)")
+    ap.add_argument("--no-scene", action="store_true", help="skip the representative-scene workload")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0,
+                    help="--impl reference: wall-clock budget; the per-step sample (batch) is halved until the run fits")
     ap.add_argument("--no-fused-adam", action="store_true",
                     help="train step: per-tensor Adam kernels instead of torch's fused multi-tensor Adam (33.0 vs 31.0 ms/step)")
     ap.add_argument("--seed-offset", type=int, default=0,
@@ -141,10 +155,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def make_host_workload(B, H, W, seed):
+def make_host_workload(B, H, W, seed, frames="smooth"):
     tdl = importlib.import_module(PKG)
     inputs, outputs, extras = tdl.synth.make_inputs(B, H, W, frame_ids=FRAME_IDS, scales=SCALES, seed=seed,
-                                                    frames="smooth", feat_channels=FEAT_C, with_noise=False)
+                                                    frames=frames, feat_channels=FEAT_C, with_noise=False)
     host = {}
     for k, v in inputs.items():
         host[("in", k)] = v
@@ -195,7 +209,13 @@ class DeviceStep:
         total = loss_dict.total()
         total.backward()
         self.loss_vec = torch.stack([v.detach() for v in loss_dict.values()])
+        self.last_outputs = outputs
         return total
+
+    def identity_frac(self):
+        """Fraction of pixels whose photometric arg-min is an identity (auto-mask) channel, per scale."""
+        S = len(FRAME_IDS) - 1
+        return [round(float((self.last_outputs[("min_index_photo", s)] < S).float().mean()), 4) for s in SCALES]
 
     def run_eager(self):
         self.total = self._step()
@@ -246,7 +266,9 @@ def whole_job_images_per_s(world, batch, steps, ms):
     return world * batch * steps / (ms * 1e-3)
 
 
-def timed_region(fn, steps, device, dist_on):
+def timed_region(fn, steps, device, dist_on, warm=None):
+    if warm is not None:
+        warm()
     if dist_on:
         torch.distributed.barrier()
     torch.cuda.synchronize(device)
@@ -261,39 +283,195 @@ def timed_region(fn, steps, device, dist_on):
     return max_over_ranks(a.elapsed_time(b), device, dist_on)
 
 
+def measure_workload(frames, args, device, rank, world, dist_on, trainable):
+    """Per-kernel device times (eager, CUDA events inside the library) and the graph-replay step time of one workload:
+    `repeats` timed regions of exactly args.steps replays, each bracketed by barrier + synchronize, max over ranks;
+    the median region is the reported figure."""
+    tdl = importlib.import_module(PKG)
+    B, H, W = args.batch, args.height, args.width
+    host = make_host_workload(B, H, W, rank_seed(rank), frames)
+    step = DeviceStep(host, B, H, W, device, trainable)
+    for _ in range(3):
+        step.run_eager()
+    torch.cuda.synchronize(device)
+    prof_steps = min(args.steps, 20)
+    tdl._lib.profile_begin()
+    for _ in range(prof_steps):
+        step.run_eager()
+    kern = tdl._lib.profile_end()
+    ident = step.identity_frac()
+    launches_per_step = sum(n for k, (n, _) in kern.items() if not k.startswith("memset")) // prof_steps
+    step.capture()
+    for _ in range(max(3, args.warmup)):
+        step.replay()
+    regions = [timed_region(step.replay, args.steps, device, dist_on) / args.steps for _ in range(max(1, args.repeats))]
+    med = statistics.median(regions)
+    return {"step": step, "host": host, "kern": kern, "prof_steps": prof_steps, "identity_frac": ident,
+            "launches_per_step": launches_per_step, "ms_per_step": med,
+            "repeats": {"n": len(regions), "steps_per_region": args.steps, "ms_per_step_median": round(med, 4),
+                        "ms_per_step_min": round(min(regions), 4), "ms_per_step_max": round(max(regions), 4),
+                        "ms_per_step_all": [round(r, 4) for r in regions]}}
+
+
+def e2e_loop(sets, n, device):
+    """n steps alternating between two device buffer sets: the copy stream uploads step i+1 while step i runs; the host
+    waits for (and reads) the losses of every step."""
+    main = torch.cuda.current_stream(device)
+    copy_stream = e2e_loop.copy_stream.get(device)
+    if copy_stream is None:
+        copy_stream = e2e_loop.copy_stream[device] = torch.cuda.Stream(device)
+    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+    for e in ev_done:
+        e.record(main)
+    with torch.cuda.stream(copy_stream):
+        copy_stream.wait_stream(main)                 # the upload of step 0 starts inside the timed region
+        sets[0].h2d()
+        ev_copied[0].record(copy_stream)
+    for i in range(n):
+        cur, k = sets[i % 2], i % 2
+        main.wait_event(ev_copied[k])
+        if i + 1 < n:
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_done[1 - k])    # the step that last read that buffer set is finished
+                sets[1 - k].h2d()
+                ev_copied[1 - k].record(copy_stream)
+        cur.replay()
+        cur.d2h()
+        ev_done[k].record(main)
+        ev_done[k].synchronize()                          # the host reads the loss of every step
+
+
+e2e_loop.copy_stream = {}
+
+
+class ImagesOnlyStep(DeviceStep):
+    """e2e variant whose per-step upload is what a data loader provides -- uint8 frames, K, inv_K -- while the feature
+    maps are produced on the device (a trainable 7x7 stride-2 conv + ReLU, the shape of the extractor's first level,
+    mono/model/mono_autoencoder/encoder.py:37) and disparities / poses are resident stand-ins for the network outputs."""
+
+    def __init__(self, host, B, H, W, device, trainable_feat=True):
+        keep = {k: v for k, v in host.items() if not (k[0] == "leaf" and (k[1] == "tgt_feat" or (isinstance(k[1], tuple) and k[1][0] == "src_feat")))}
+        super().__init__(keep, B, H, W, device, True)
+        self.frames_u8 = {f: (host[("in", ("color", f, 0))] * 255).round().to(torch.uint8).pin_memory() for f in FRAME_IDS}
+        self.frames_dev = {f: torch.empty_like(v, device=device) for f, v in self.frames_u8.items()}
+        self.host = {k: v for k, v in self.host.items() if k[0] == "in" and not isinstance(k[1], tuple)}   # K, inv_K
+        g = torch.Generator().manual_seed(0)
+        self.stem = (torch.randn(FEAT_C, 3, 7, 7, generator=g) * 0.1).to(device).requires_grad_(True)
+
+    def _step(self):
+        b = self.buf
+        for k in self.grad_keys:
+            b[k].grad = None
+        self.stem.grad = None
+        imgs = {f: self.frames_dev[f].float() * (1.0 / 255.0) for f in FRAME_IDS}
+        inputs = {k[1]: v for k, v in b.items() if k[0] == "in" and not isinstance(k[1], tuple)}
+        for f in FRAME_IDS:
+            inputs[("color", f, 0)] = imgs[f]
+        outputs = {k[1]: v for k, v in b.items() if k[0] == "leaf"}
+        feats = {f: torch.relu(torch.nn.functional.conv2d(imgs[f], self.stem, stride=2, padding=3)) for f in FRAME_IDS}
+        loss_dict = self.net.compute_losses_fm(inputs, outputs, None, feats[0], {f: feats[f] for f in FRAME_IDS[1:]})
+        total = loss_dict.total()
+        total.backward()
+        self.loss_vec = torch.stack([v.detach() for v in loss_dict.values()])
+        self.last_outputs = outputs
+        return total
+
+    def h2d(self):
+        for f, v in self.frames_u8.items():
+            self.frames_dev[f].copy_(v, non_blocking=True)
+        for k, v in self.host.items():
+            self.buf[k].detach().copy_(v, non_blocking=True)
+
+    def h2d_bytes(self):
+        return sum(v.numel() for v in self.frames_u8.values()) + sum(v.numel() * v.element_size() for v in self.host.values())
+
+
+def bind_host_near_gpu(local):
+    """Best effort: run this process on the CPUs that are NUMA-local to its GPU (sysfs local_cpulist of the PCI
+    device), so that the pinned staging buffers it first-touches sit on that node -- at 8 ranks the e2e figure is
+    otherwise bound by cross-socket host memory traffic rather than by the path."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return sorted(allowed)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ CPU arms
-def cpu_port_step(rec_builder):
-    """One fwd+bwd of the CPU oracle (the port of the reference's mono_fm loss) on a fresh copy of the inputs."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from golden_util import run_restatement
-    rec = rec_builder()
-    loss, _, _ = run_restatement(rec)
-    sum(loss.values()).backward()
-    return float(sum(v.detach() for v in loss.values()))
-
-
-def cpu_record(B, H, W, seed):
+def cpu_record(B, H, W, seed, frames="smooth"):
     tdl = importlib.import_module(PKG)
     inputs, outputs, extras = tdl.synth.make_inputs(B, H, W, frame_ids=FRAME_IDS, scales=SCALES, seed=seed,
-                                                    frames="smooth", feat_channels=FEAT_C, with_noise=False)
+                                                    frames=frames, feat_channels=FEAT_C, with_noise=False)
     leaves = dict(outputs)
     leaves["tgt_feat"] = extras["tgt_feat"]
     for f, t in extras["src_feats"].items():
         leaves[("src_feat", f)] = t
     return {"inputs": inputs, "leaves": leaves,
-            "meta": dict(kind="fm", B=B, H=H, W=W, frames="smooth", C=FEAT_C, seed=seed, opt=opt_dict(B, H, W))}
+            "meta": dict(kind="fm", B=B, H=H, W=W, frames=frames, C=FEAT_C, seed=seed, opt=opt_dict(B, H, W))}
 
 
-def time_cpu_port(B, H, W, steps, warmup):
+def cpu_arm_kind():
+    """"reference": the reference's own modules are reachable (oracle/_ref on the GPU box, /root/reference in the
+    build container) and are what gets timed; "port": oracle/restatement.py (bit-identical restatement)."""
+    try:
+        from oracle import ref_loader
+        return "reference" if ref_loader.reference_available() else "port"
+    except Exception:
+        return "port"
+
+
+def cpu_step(rec, kind):
+    """One forward + backward of the reference's mono_fm loss on the host cores, on fresh leaf tensors."""
+    if kind == "reference":
+        from oracle import ref_loader
+        meta = rec["meta"]
+        opt = ref_loader.default_opt(meta["B"], meta["H"], meta["W"])
+        opt.update(meta["opt"])
+        leaves = {k: v.clone().requires_grad_(True) for k, v in rec["leaves"].items()}
+        outputs = {k: v for k, v in leaves.items() if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam")}
+        src = {f: leaves[("src_feat", f)] for f in FRAME_IDS[1:]}
+        loss = ref_loader.run_reference_loss("fm", opt, dict(rec["inputs"]), outputs, leaves["tgt_feat"], src)
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from golden_util import run_restatement
+        loss, _, _ = run_restatement(rec)
+    total = sum(v.mean() for v in loss.values())         # batch_processor (mono/apis/trainer.py:39-48)
+    total.backward()
+    return float(total.detach())
+
+
+def time_cpu_arm(B, H, W, steps, warmup, kind, budget_s=None):
+    """-> (images/s, s/step, batch actually used).  With a budget the per-step sample (batch) is halved until
+    (steps + warmup) steps fit, judged from the first warm-up step."""
     torch.set_num_threads(os.cpu_count() or 1)
-    rec = cpu_record(B, H, W, 4321)
-    for _ in range(warmup):
-        cpu_port_step(lambda: rec)
+    import warnings
+    warnings.filterwarnings("ignore", message="Default grid_sample")
+    while True:
+        rec = cpu_record(B, H, W, 4321)
+        t0 = time.perf_counter()
+        cpu_step(rec, kind)
+        first = time.perf_counter() - t0
+        if budget_s is None or B == 1 or first * (steps + warmup) <= budget_s:
+            break
+        B = max(1, B // 2)
+    for _ in range(max(0, warmup - 1)):
+        cpu_step(rec, kind)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_port_step(lambda: rec)
+        cpu_step(rec, kind)
     dt = time.perf_counter() - t0
-    return B * steps / dt, dt / steps
+    return B * steps / dt, dt / steps, B
 
 
 # ------------------------------------------------------------------------------------------------ train step
@@ -415,7 +593,8 @@ def config_dict(args, trainable):
     return {"workload": f"mono_fm loss fwd+bwd (cfg_kitti_fm): {args.height}x{args.width}, batch {args.batch}/GPU, "
                         f"frames [0,-1,1], 4 scales, {FEAT_C}-ch features at H/2xW/2, "
                         f"{'trainable' if trainable else 'frozen'} extractor features, reference-faithful outputs "
-                        "(warped images/features + int64 min_index materialised), in-kernel Philox automask noise",
+                        "(warped images/features + int64 min_index materialised), in-kernel Philox automask noise; "
+                        "value = 'smooth' synthetic frames (SURVEY 8d), `scene` block = rendered moving-camera frames",
             "global_batch": args.batch * args.gpus, "per_gpu_batch": args.batch,
             "height": args.height, "width": args.width, "parallelism": f"dp{args.gpus} (batch-sharded, no collective)",
             "l2_policy": "per-step working set (~0.6 GB at batch 8) exceeds the 126 MB L2; inputs are re-streamed "
@@ -458,17 +637,22 @@ def run():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-        ips, spstep = time_cpu_port(args.cpu_batch, args.height, args.width, steps, warm)
+        kind = cpu_arm_kind()
+        steps, warm = max(1, args.steps), max(0, args.warmup)
+        ips, spstep, used_b = time_cpu_arm(args.batch, args.height, args.width, steps, warm, kind, args.ref_budget_s)
         cores = os.cpu_count() or 1
+        what = ("the UNMODIFIED reference modules (oracle/_ref: mono/model/mono_fm/net.py compute_losses + autograd backward)"
+                if kind == "reference" else "oracle/restatement.py (bit-identical port; the reference modules did not travel)")
+        cfg = config_dict(args, trainable)
+        cfg["reference_arm"] = (f"batch {used_b} per step (asked {args.batch}), {steps} timed steps after {warm} warm-ups, "
+                                f"torch CPU ops on {cores} threads, features supplied as tensors like the GPU arm")
         line = {"impl": "reference", "metric": "fused_loss_fwd_bwd_images_per_s", "value": ips, "unit": "images/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": spstep * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config_dict(args, trainable),
-                "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                                 "sample": f"batch {args.cpu_batch} of the same {args.height}x{args.width} workload per "
-                                           f"step, {steps} steps, torch CPU ops on {cores} threads "
-                                           "(oracle/restatement.py; /root/reference is absent on the GPU box)"},
+                "config": cfg,
+                "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
+                                 "sample": f"batch {used_b} of the same {args.height}x{args.width} workload per step, "
+                                           f"{steps} steps after {warm} warm-ups; {what}"},
                 "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         return line
@@ -484,32 +668,18 @@ def run():
     tdl._lib.lib()                                   # fail loudly if libtdl.so is missing
 
     B, H, W = args.batch, args.height, args.width
-    host = make_host_workload(B, H, W, rank_seed(rank))
+    bind_host_near_gpu(local)                # pinned staging buffers are first touched by this process: keep it NUMA-local
     side = torch.cuda.Stream(device)
     torch.cuda.set_stream(side)              # every launch, copy and timing event below is on this stream
-    step = DeviceStep(host, B, H, W, device, trainable)
-
-    # ---- per-kernel device time (CUDA events on the launch stream), eager, before the graph is built
-    for _ in range(3):
-        step.run_eager()
-    torch.cuda.synchronize(device)
-    prof_steps = min(args.steps, 20)
-    tdl._lib.profile_begin()
-    for _ in range(prof_steps):
-        step.run_eager()
-    kern = tdl._lib.profile_end()
-    launches_per_step = sum(n for k, (n, _) in kern.items() if not k.startswith("memset")) // prof_steps
-
-    # ---- value: device-resident inputs, CUDA-graph replay
-    step.capture()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()          # samples cover the warm-up replays (same load) and the timed region
-    for _ in range(max(3, args.warmup)):
-        step.replay()
-    ms = timed_region(step.replay, args.steps, device, dist_on)
+        sampler.start()                      # covers the warm-up replays and every timed region of both workloads
+    smooth = measure_workload("smooth", args, device, rank, world, dist_on, trainable)
+    scene = None if args.no_scene else measure_workload("scene", args, device, rank, world, dist_on, trainable)
     clocks = sampler.stop() if rank == 0 else None
-    value = whole_job_images_per_s(world, B, args.steps, ms)
+    step, host = smooth["step"], smooth["host"]
+    ms_step = smooth["ms_per_step"]
+    value = world * B / (ms_step * 1e-3)
 
     # ---- e2e: host (pinned) buffers -> H2D of every input of the step -> step -> D2H of the loss scalars, with a
     #      host synchronisation per step like the reference's per-iteration .item() (mono/apis/trainer.py:52-54).
@@ -518,40 +688,25 @@ def run():
     for _ in range(3):
         step2.run_eager()
     step2.capture()
-    sets = [step, step2]
-    copy_stream = torch.cuda.Stream(device)
-    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def e2e_loop(n):
-        main = torch.cuda.current_stream(device)
-        for e in ev_done:
-            e.record(main)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_stream(main)                 # the upload of step 0 starts inside the timed region
-            sets[0].h2d()
-            ev_copied[0].record(copy_stream)
-        for i in range(n):
-            cur, k = sets[i % 2], i % 2
-            main.wait_event(ev_copied[k])
-            if i + 1 < n:
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(ev_done[1 - k])    # the step that last read that buffer set is finished
-                    sets[1 - k].h2d()
-                    ev_copied[1 - k].record(copy_stream)
-            cur.replay()
-            cur.d2h()
-            ev_done[k].record(main)
-            ev_done[k].synchronize()                          # the host reads the loss of every step
-
-    e2e_loop(4)
     e2e_steps = min(args.steps, 40)
-    ms_e2e = timed_region(lambda: e2e_loop(e2e_steps), 1, device, dist_on)
+    ms_e2e = timed_region(lambda: e2e_loop([step, step2], e2e_steps, device), 1, device, dist_on, warm=lambda: e2e_loop([step, step2], 4, device))
     e2e_value = whole_job_images_per_s(world, B, e2e_steps, ms_e2e)
+    del step2
+
+    # ---- e2e_images_only: what a data loader hands over (uint8 frames, K, inv_K) is uploaded; disparities / poses are
+    #      resident stand-ins for the network outputs, the features come from a conv stem ON THE DEVICE
+    io_a, io_b = ImagesOnlyStep(host, B, H, W, device), ImagesOnlyStep(host, B, H, W, device)
+    for st_ in (io_a, io_b):
+        for _ in range(3):
+            st_.run_eager()
+        st_.capture()
+    ms_io = timed_region(lambda: e2e_loop([io_a, io_b], e2e_steps, device), 1, device, dist_on, warm=lambda: e2e_loop([io_a, io_b], 4, device))
+    io_value = whole_job_images_per_s(world, B, e2e_steps, ms_io)
+    io_bytes = io_a.h2d_bytes()
+    del io_a, io_b
 
     train = None
     if not args.no_train:
-        del step2, sets
         torch.cuda.empty_cache()
         train = train_step_bench(args, device, rank, world, dist_on)
 
@@ -560,7 +715,7 @@ def run():
             torch.distributed.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline: dominant kernel of the representative ("scene") workload
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -568,43 +723,57 @@ def run():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     S = len(FRAME_IDS) - 1
     alg = algorithmic_bytes(B, H, W, S, FEAT_C, len(SCALES), trainable)
-    kernels = {}
-    for name, (n, total_ms) in kern.items():
-        avg_us = total_ms / n * 1e3
-        per_step_us = total_ms / prof_steps * 1e3
-        row = {"launches_per_step": n / prof_steps, "avg_us": round(avg_us, 2), "us_per_step": round(per_step_us, 2)}
-        if name in alg and alg[name]:
-            row["alg_bytes"] = alg[name]
-            row["gbs"] = round(alg[name] / (avg_us * 1e-6) / 1e9, 1)
-        kernels[name] = row
-    tot_us = sum(r["us_per_step"] for r in kernels.values())
-    for r in kernels.values():
-        r["share"] = round(r["us_per_step"] / tot_us, 3)
-    dom = max((k for k in kernels if "alg_bytes" in kernels[k]), key=lambda k: kernels[k]["us_per_step"])
-    achieved = kernels[dom]["gbs"]
     total_alg = sum(alg[k] for k in ("photo_fwd", "photo_bwd", "feat_fwd", "feat_bwd", "memset_dsrc"))
+
+    def kernel_table(m):
+        kernels = {}
+        for name, (n, total_ms) in m["kern"].items():
+            avg_us = total_ms / n * 1e3
+            row = {"launches_per_step": n / m["prof_steps"], "avg_us": round(avg_us, 2),
+                   "us_per_step": round(total_ms / m["prof_steps"] * 1e3, 2)}
+            if name in alg and alg[name]:
+                row["alg_bytes"] = alg[name]
+                row["gbs"] = round(alg[name] / (avg_us * 1e-6) / 1e9, 1)
+            kernels[name] = row
+        tot_us = sum(r["us_per_step"] for r in kernels.values())
+        for r in kernels.values():
+            r["share"] = round(r["us_per_step"] / tot_us, 3)
+        return kernels
+
+    def whole_step(m):
+        gbs = total_alg / (m["ms_per_step"] * 1e-3) / 1e9
+        return {"alg_bytes": total_alg, "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+
+    k_smooth = kernel_table(smooth)
+    dom_src, dom_tab = ("scene", kernel_table(scene)) if scene else ("smooth", k_smooth)
+    dom = max((k for k in dom_tab if "alg_bytes" in dom_tab[k]), key=lambda k: dom_tab[k]["us_per_step"])
+    achieved = dom_tab[dom]["gbs"]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed
         tj = json.load(open(tpath))  # `ncu --set full` capture of this same default workload
-        if tj.get("workload") == [B, H, W, S, FEAT_C] and dom in tj.get("kernels", {}):
-            traffic = tj["kernels"][dom]
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        if tj.get("workload") == [B, H, W, S, FEAT_C] and dom in tj.get(dom_src, tj).get("kernels", {}):
+            traffic = tj.get(dom_src, tj)["kernels"][dom]
+    roofline = {"bound": "hbm", "kernel": dom, "workload": dom_src, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg[dom],
-                "whole_step": {"alg_bytes": total_alg, "gbs": round(total_alg / (ms / args.steps * 1e-3) / 1e9, 1),
-                               "frac": round(total_alg / (ms / args.steps * 1e-3) / 1e9 / peak, 4)},
+                "whole_step": whole_step(scene) if scene else whole_step(smooth),
+                "whole_step_smooth": whole_step(smooth),
+                "kernels": dom_tab}
+
+    def block(m, kernels):
+        return {"images_per_s": round(world * B / (m["ms_per_step"] * 1e-3), 1), "ms_per_step": round(m["ms_per_step"], 4),
+                "repeats": m["repeats"], "identity_frac": m["identity_frac"], "launches_per_step": m["launches_per_step"],
                 "kernels": kernels}
 
-    cpu = None
+    cpu = eager = None
     if world == 1 and not args.no_cpu_baseline:
-        ips, spstep = time_cpu_port(args.cpu_batch, H, W, 8, 1)
-        cpu = {"value": round(ips, 3), "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"batch {args.cpu_batch} of the same {H}x{W} workload, 8 timed steps after 1 warm-up "
-                         f"({spstep:.2f} s/step), oracle/restatement.py on all host threads"}
-
-    eager = None
-    if world == 1 and not args.no_cpu_baseline:
+        kind = cpu_arm_kind()
+        ips, spstep, used_b = time_cpu_arm(args.cpu_batch, H, W, 8, 1, kind)
+        cpu = {"value": round(ips, 3), "unit": "images/s", "cores": os.cpu_count() or 1, "kind": kind,
+               "sample": f"batch {used_b} of the same {H}x{W} workload, 8 timed steps after 1 warm-up "
+                         f"({spstep:.2f} s/step), " + ("the unmodified reference modules (oracle/_ref)" if kind == "reference"
+                                                         else "oracle/restatement.py") + " on all host threads"}
         try:
             ips, spstep = time_eager_gpu_port(B, H, W, device)
             eager = {"value": round(ips, 1), "unit": "images/s", "ms_per_step": round(spstep * 1e3, 2), "kind": "port",
@@ -614,13 +783,20 @@ def run():
             eager = {"unavailable": f"{type(exc).__name__}: {exc}"}
 
     line = {"metric": "fused_loss_fwd_bwd_images_per_s", "value": round(value, 1), "unit": "images/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 4),
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 4),
+            "repeats": smooth["repeats"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, trainable), "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": step.h2d_bytes(),
                     "d2h_bytes_per_step": step.losses_host.numel() * 4, "ms_per_step": round(ms_e2e / e2e_steps, 4),
                     "steps": e2e_steps},
-            "gpu_launches": launches_per_step * args.steps,
+            "e2e_images_only": {"value": round(io_value, 1), "unit": "images/s", "h2d_bytes_per_step": io_bytes,
+                                "d2h_bytes_per_step": 12 * 4, "ms_per_step": round(ms_io / e2e_steps, 4), "steps": e2e_steps,
+                                "what": "uint8 frames + K + inv_K uploaded per step; uint8 -> fp32 conversion, a trainable 7x7/2 conv + "
+                                        "ReLU feature stem (3 frames), loss fwd + bwd through the stem, on the device"},
+            "gpu_launches": smooth["launches_per_step"] * args.steps * smooth["repeats"]["n"],
+            "gpu_launches_per_step": smooth["launches_per_step"],
+            "smooth": block(smooth, k_smooth), "scene": block(scene, dom_tab) if scene else None,
             "roofline": roofline, "cpu_baseline": cpu, "eager_torch_gpu_baseline": eager,
             "train_step": train}
     if dist_on:
