@@ -97,9 +97,11 @@ def load():
 
 
 @contextlib.contextmanager
-def cpu_cuda_shim():
-    """``Tensor.cuda`` -> identity while the reference loss runs without a GPU."""
-    if torch.cuda.is_available():
+def cpu_cuda_shim(force=False):
+    """``Tensor.cuda`` -> identity while the reference loss runs on CPU tensors (always when there is no GPU;
+    ``force`` for the CPU arm of bench.py on the GPU box, where the reference's hard-coded ``.cuda()`` calls would
+    otherwise move its constants to the device)."""
+    if torch.cuda.is_available() and not force:
         yield
         return
     orig = torch.Tensor.cuda
@@ -186,7 +188,7 @@ def run_reference_loss(kind, opt, inputs, outputs, tgt_feat=None, src_feats=None
         for f, t in src_feats.items():
             table[inputs[("color", f, 0)].data_ptr()] = t
         (net.extractor if kind == "fm" else net.Encoder).table = table
-    with cpu_cuda_shim():
+    with cpu_cuda_shim(force=not inputs[("color", 0, 0)].is_cuda):
         if kind in ("inpaint", "tripled", "joint"):
             return net.compute_losses(inputs, outputs, features)
         return net.compute_losses(inputs, outputs)

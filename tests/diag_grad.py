@@ -40,6 +40,10 @@ for k, leaf in ref_leaves.items():
     top = e2.topk(min(10, e2.numel()))
     w = g.shape[-1]
     hh = g.shape[-2]
-    print(k, "rel", f"{rel_l2(g, r):.2e}", "top10 energy", f"{float(top.values.sum() / e2.sum()):.3f}",
+    srt = e2.double().sort(descending=True).values
+    rest = (srt.sum() - srt.cumsum(0)).clamp_min(0).sqrt() / r.double().norm()
+    need = int((rest > 1e-4).sum()) + 1 if float(rel_l2(g, r)) > 1e-4 else 0
+    print(k, "cells to drop for 1e-4:", need, "of", e2.numel(), end="  ")
+    print("rel", f"{rel_l2(g, r):.2e}", "top10 energy", f"{float(top.values.sum() / e2.sum()):.3f}",
           "at", [(int(i) // (w * hh), int(i) // w % hh, int(i) % w) for i in top.indices[:4]],
           "err", [f"{float(x):.2e}" for x in e[top.indices[:4]]], "ref", [f"{float(x):.2e}" for x in r.flatten()[top.indices[:4]]])

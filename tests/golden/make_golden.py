@@ -87,7 +87,7 @@ def run_reference(kind, B, H, W, frames, C, seed):
                 outputs[("auto_res_img", 0, 0)] = a
             inputs[("mask", 0, 0)] = mask
     torch.manual_seed(seed)          # the reference draws automask noise from the global CPU RNG
-    with ref_loader.cpu_cuda_shim():
+    with ref_loader.cpu_cuda_shim(force=True):
         if kind in ("inpaint", "tripled", "joint"):
             loss_dict = net.compute_losses(inputs, outputs, features)
         else:

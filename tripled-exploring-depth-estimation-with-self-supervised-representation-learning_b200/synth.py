@@ -241,7 +241,7 @@ def _make_scene_inputs(g, B, H, W, frame_ids, scales, feat_channels, with_noise)
     inputs, outputs, extras = {}, {}, {}
     base = _box(_box(torch.rand(B, 3, H + 16, W + 16, generator=g), 9), 9)
     base = _unit(base)[:, :, 8:8 + H, 8:8 + W]
-    fine = _box(torch.rand(B, 3, H, W, generator=g), 3)            # finer texture: keeps SSIM informative at 1-pixel shifts
+    fine = _box(_box(torch.rand(B, 3, H, W, generator=g), 3), 3) * 1.5   # finer texture: keeps SSIM informative at 1-pixel shifts
     target = (0.8 * base + 0.2 * fine).clamp(0, 1).contiguous()
     inputs[("color", 0, 0)] = target
     K, inv_K = kitti_intrinsics(B, H, W)
