@@ -205,7 +205,7 @@ const char* tdl_strerror(int code);
 /* Process-wide switches for tests and kernel experiments (the defaults are the product path).  They are
  * initialised once from the environment (TDL_NO_TMA, TDL_FUSED_FWD, TDL_PHOTO_SPARSE_MAX, TDL_FEAT_ATOMIC,
  * TDL_FEAT_CHUNK) and afterwards only change through this call -- the entry points never call getenv().
- * Names: "no_tma", "fused_fwd", "photo_sparse_max", "feat_atomic", "feat_chunk". */
+ * Names: "no_tma", "fused_fwd", "photo_sparse_max", "feat_atomic", "feat_chunk", "photo_v1" (round-1 kernels). */
 int tdl_set_option(const char* name, int value);
 int tdl_get_option(const char* name, int* value);
 /* number of CUDA kernels (not memsets) one call launches -- used by bench.py's gpu_launches */

@@ -19,10 +19,10 @@ namespace {
 
 // ---- process-wide tuning / test switches.  Read from the environment ONCE (first use) and afterwards only changed through
 // tdl_set_option(): the entry points below are on the training step's host path and must not call getenv().
-enum Opt { kOptNoTma = 0, kOptFusedFwd, kOptSparseMax, kOptFeatAtomic, kOptFeatChunk, kOptCount };
-const char* const kOptNames[kOptCount] = {"no_tma", "fused_fwd", "photo_sparse_max", "feat_atomic", "feat_chunk"};
-const char* const kOptEnv[kOptCount] = {"TDL_NO_TMA", "TDL_FUSED_FWD", "TDL_PHOTO_SPARSE_MAX", "TDL_FEAT_ATOMIC", "TDL_FEAT_CHUNK"};
-const int kOptDefault[kOptCount] = {0, 0, 128, 0, 0};
+enum Opt { kOptNoTma = 0, kOptFusedFwd, kOptSparseMax, kOptFeatAtomic, kOptFeatChunk, kOptPhotoV1, kOptCount };
+const char* const kOptNames[kOptCount] = {"no_tma", "fused_fwd", "photo_sparse_max", "feat_atomic", "feat_chunk", "photo_v1"};
+const char* const kOptEnv[kOptCount] = {"TDL_NO_TMA", "TDL_FUSED_FWD", "TDL_PHOTO_SPARSE_MAX", "TDL_FEAT_ATOMIC", "TDL_FEAT_CHUNK", "TDL_PHOTO_V1"};
+const int kOptDefault[kOptCount] = {0, 0, 128, 0, 0, 0};
 std::atomic<int> g_opt[kOptCount];
 std::once_flag g_opt_once;
 
@@ -134,6 +134,7 @@ int check_photo(const tdl_photo_args* a, bool bwd, PhotoDev* d) {
     d->automask = a->automask != 0;
     d->use_tma = !opt(kOptNoTma);
     d->split_fwd = !opt(kOptFusedFwd);
+    d->v1 = opt(kOptPhotoV1) != 0;
     {
         // tiles with <= 128 selected windows (of 1156 incl. halo, all frames) take the scatter path; 128 is also the hard
         // limit (9 live pixels per window must fit the tile's list).  Tests: 0 forces the dense backward everywhere.
@@ -328,7 +329,7 @@ int tdl_photo_fwd(const tdl_photo_args* a, tdl_stream_t stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (photo_fwd_can_split(d)) {                             // (photo_warp clears the accumulators itself)
         TDL_KERNEL("photo_warp", launch_photo_warp(d, st));
-        TDL_KERNEL("photo_score", launch_photo_score(d, st));
+        TDL_KERNEL("photo_score", d.v1 ? launch_photo_score(d, st) : launch_photo_score2(d, st));
     } else {
         TDL_KERNEL("memset", cudaMemsetAsync(d.acc, 0, (size_t)a->nscales * a->B * 4 * sizeof(double), st));
         TDL_KERNEL("photo_fwd", launch_photo_fwd(d, st));

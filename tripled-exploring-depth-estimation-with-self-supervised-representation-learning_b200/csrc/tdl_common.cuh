@@ -56,6 +56,11 @@ TDL_DEV float sqrt_fast(float x) {
     const float s = x * r;
     return fmaf(fmaf(-s, s, x), 0.5f * r, s);
 }
+// 1/d to ~1 ulp without the IEEE slow-path call of __frcp_rn (d in [1e-7, 1e4]): MUFU seed + one Newton step
+TDL_DEV float rcp_newton(float d) {
+    const float r = rcp_approx(d);
+    return fmaf(fmaf(-d, r, 1.f), r, r);
+}
 // division by a constant whose reciprocal rc = fl(1/c) is known
 TDL_DEV float div_const(float n, float c, float rc) {
     const float q = n * rc;
@@ -138,8 +143,30 @@ struct Proj {
     float mx, my;         // d ix / d u and d iy / d v (0 where the coordinate was clipped)
 };
 
+// image-size constants of Project / grid_sample: computed ONCE per kernel (the IEEE divisions compile to a call with a
+// slow path; inside a loop with many live registers every such call spills them)
+struct ProjConst {
+    float wm1, hm1, rwm1, rhm1;   // W-1, H-1 and their reciprocals
+    float Wf, Hf;
+    float sx, sy;                 // d ix / d u, d iy / d v where the coordinate is not clipped
+    int align_corners;
+};
+TDL_DEV ProjConst make_proj_const(int H, int W, int align_corners) {
+    ProjConst c;
+    c.wm1 = static_cast<float>(W - 1);
+    c.hm1 = static_cast<float>(H - 1);
+    c.rwm1 = 1.f / c.wm1;
+    c.rhm1 = 1.f / c.hm1;
+    c.Wf = static_cast<float>(W);
+    c.Hf = static_cast<float>(H);
+    c.sx = align_corners ? 1.f : c.Wf / c.wm1;
+    c.sy = align_corners ? 1.f : c.Hf / c.hm1;
+    c.align_corners = align_corners;
+    return c;
+}
+
 template <bool kGrad>
-TDL_DEV Proj project(const Geo& g, const float* P, int H, int W, int align_corners) {
+TDL_DEV Proj project(const Geo& g, const float* P, const ProjConst& c) {
     Proj o;
     const float p0 = P[0] * g.X0 + P[1] * g.X1 + P[2] * g.X2 + P[3];          // layers.py:75
     const float p1 = P[4] * g.X0 + P[5] * g.X1 + P[6] * g.X2 + P[7];
@@ -151,32 +178,34 @@ TDL_DEV Proj project(const Geo& g, const float* P, int H, int W, int align_corne
         o.u = fmaf(fmaf(-o.z, qu, p0), rz, qu);
         o.v = fmaf(fmaf(-o.z, qv, p1), rz, qv);
     }
-    const float wm1 = static_cast<float>(W - 1), hm1 = static_cast<float>(H - 1);
-    const float gx = __fmul_rn(__fsub_rn(div_const(o.u, wm1, 1.f / wm1), 0.5f), 2.0f);   // layers.py:79-81
-    const float gy = __fmul_rn(__fsub_rn(div_const(o.v, hm1, 1.f / hm1), 0.5f), 2.0f);
+    const float gx = __fmul_rn(__fsub_rn(div_const(o.u, c.wm1, c.rwm1), 0.5f), 2.0f);   // layers.py:79-81
+    const float gy = __fmul_rn(__fsub_rn(div_const(o.v, c.hm1, c.rhm1), 0.5f), 2.0f);
     float ix, iy;
-    if (align_corners) {                                                      // grid_sampler_unnormalize
-        ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), wm1);             // x/2 == x*0.5 exactly
-        iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), hm1);
+    if (c.align_corners) {                                                    // grid_sampler_unnormalize
+        ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), c.wm1);           // x/2 == x*0.5 exactly
+        iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), c.hm1);
     } else {
-        ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), static_cast<float>(W)), 1.f), 0.5f);
-        iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), static_cast<float>(H)), 1.f), 0.5f);
+        ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), c.Wf), 1.f), 0.5f);
+        iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), c.Hf), 1.f), 0.5f);
     }
     if (kGrad) {
         // clip_coordinates_set_grad: zero gradient when ix <= 0 or ix >= size-1
-        const float sx = align_corners ? 1.f : static_cast<float>(W) / wm1;
-        const float sy = align_corners ? 1.f : static_cast<float>(H) / hm1;
-        o.mx = (ix <= 0.f || ix >= wm1) ? 0.f : sx;
-        o.my = (iy <= 0.f || iy >= hm1) ? 0.f : sy;
+        o.mx = (ix <= 0.f || ix >= c.wm1) ? 0.f : c.sx;
+        o.my = (iy <= 0.f || iy >= c.hm1) ? 0.f : c.sy;
         if (!(ix == ix)) o.mx = 0.f;
         if (!(iy == iy)) o.my = 0.f;
     }
     // padding_mode="border": clip to [0, size-1]; NaN -> 0 keeps the gather in range
-    ix = fminf(wm1, fmaxf(ix, 0.f));
-    iy = fminf(hm1, fmaxf(iy, 0.f));
+    ix = fminf(c.wm1, fmaxf(ix, 0.f));
+    iy = fminf(c.hm1, fmaxf(iy, 0.f));
     o.ix = ix;
     o.iy = iy;
     return o;
+}
+
+template <bool kGrad>
+TDL_DEV Proj project(const Geo& g, const float* P, int H, int W, int align_corners) {
+    return project<kGrad>(g, P, make_proj_const(H, W, align_corners));
 }
 
 struct Bilin {            // ATen grid_sampler_2d bilinear taps

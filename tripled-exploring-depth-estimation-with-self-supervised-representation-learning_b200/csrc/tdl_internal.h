@@ -39,6 +39,7 @@ struct PhotoDev {
     int automask, align_corners;
     int use_tma;                 // stage image tiles with TMA box copies when the tensors allow it
     int split_fwd;               // forward = warp kernel + TMA-staged scoring kernel (needs materialised warps)
+    int v1;                      // use the round-1 scoring kernel (A/B comparisons and tests)
     int sparse_max;              // backward: tiles with at most this many selected windows (of 1156 incl. halo) scatter
                                  // their adjoint instead of running the dense box-sum gather (auto-masked regions)
     float min_disp, range;
@@ -140,7 +141,8 @@ cudaError_t launch_recon_bwd(const ReconArgsDev& a, cudaStream_t st);
 cudaError_t launch_photo_fwd(const PhotoDev& p, cudaStream_t st);
 bool photo_fwd_can_split(const PhotoDev& p);
 cudaError_t launch_photo_warp(const PhotoDev& p, cudaStream_t st);
-cudaError_t launch_photo_score(const PhotoDev& p, cudaStream_t st);
+cudaError_t launch_photo_score(const PhotoDev& p, cudaStream_t st);      // round-1 strip kernel (option photo_v1)
+cudaError_t launch_photo_score2(const PhotoDev& p, cudaStream_t st);     // register micro-tile kernel (tdl_photo2.cu)
 cudaError_t launch_photo_bwd(const PhotoDev& p, cudaStream_t st);
 cudaError_t launch_smooth_fwd(const SmoothDev& p, cudaStream_t st);
 cudaError_t launch_smooth_bwd(const SmoothDev& p, cudaStream_t st);
