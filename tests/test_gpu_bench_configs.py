@@ -20,13 +20,13 @@ def test_config2_fm_b8_192x640_c64(frames):
     """cfg_kitti_fm (config/cfg_kitti_fm.py): mono_fm loss, batch 8, 192x640, 64-channel features at 96x320 --
     bench.py's headline workload ("smooth") and its representative-scene workload ("scene")."""
     rec = _synthetic_record("fm", 8, 192, 640, 64, 1234, frames=frames)
-    _check(rec, f"config2-fm-{frames}-8x192x640-C64")
+    _check(rec, f"config2-fm-{frames}-8x192x640-C64", floor=True)
 
 
 def test_config4_fm_b4_320x1024_c64():
     """cfg_kitti_fm high resolution: batch 4, 320x1024, 64-channel features at 160x512."""
     rec = _synthetic_record("fm", 4, 320, 1024, 64, 1244, frames="smooth")
-    _check(rec, "config4-fm-smooth-4x320x1024-C64")
+    _check(rec, "config4-fm-smooth-4x320x1024-C64", floor=True)
 
 
 def test_config3_tripled_b2_192x640_real_widths():
@@ -34,7 +34,7 @@ def test_config3_tripled_b2_192x640_real_widths():
     level widths (64 / 256 / 512 / 1024 / 2048 channels at H/2 .. H/32) through tdl_edge_smooth_*, the masked
     reconstruction at four scales through tdl_recon_* (16 erased 16x16 holes) and auto_res_loss."""
     rec = _synthetic_record("tripled", 2, 192, 640, 64, 1245, frames="smooth", level_widths=(256, 512, 1024, 2048), hole=16)
-    _check(rec, "config3-tripled-smooth-2x192x640")
+    _check(rec, "config3-tripled-smooth-2x192x640", floor=True)
 
 
 # ------------------------------------------------------------------------------------------------ Philox path

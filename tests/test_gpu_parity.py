@@ -83,7 +83,36 @@ def _trimmed_rel_l2(a, b, k):
 REPORT = os.environ.get("TDL_PARITY_REPORT")      # JSON lines, one per checked case (tests/parity_report.py formats them)
 
 
-def _check(rec, tag, golden=None, img_rtol=IMG_RTOL, grad_rtol=GRAD_RTOL, flip_budget=FLIP_BUDGET):
+def _reference_cross_device_floor(rec, forced, ref_leaves, n_trim_of):
+    """The REFERENCE against ITSELF on another device: oracle.restatement (bit-identical to the reference's ops) run as
+    eager PyTorch on the GPU, same inputs, same imposed arg-min selection, against its CPU run.  Its gradient error is the
+    floor any fp32 implementation on another device is subject to (kinks decided by rounding); returned per leaf as
+    (untrimmed, trimmed) relative L2."""
+    dev = "cuda"
+    rec_d = {"inputs": {k: v.to(dev) for k, v in rec["inputs"].items()},
+             "leaves": {k: v.to(dev) for k, v in rec["leaves"].items()}, "meta": rec["meta"]}
+    import oracle.restatement as R
+    draw = R.draw_automask_noise
+
+    def draw_dev(spec, batch, generator=None, dtype=torch.float32):
+        return {s: {f: n.to(dev) for f, n in d.items()} for s, d in draw(spec, batch, generator, dtype).items()}
+    R.draw_automask_noise = draw_dev
+    try:
+        forced_d = {k: v.to(dev) for k, v in forced.items()}
+        loss_d, _, leaves_d = run_restatement(rec_d, forced=forced_d)
+        sum(v.mean() for v in loss_d.values()).backward()
+    finally:
+        R.draw_automask_noise = draw
+    out = {}
+    for k, leaf in ref_leaves.items():
+        if leaf.grad is None or leaves_d[k].grad is None or float(leaf.grad.abs().max()) == 0.0:
+            continue
+        gd = leaves_d[k].grad.detach().cpu()
+        out[k] = (rel_l2(gd, leaf.grad), _trimmed_rel_l2(gd, leaf.grad, n_trim_of(leaf.grad)))
+    return out
+
+
+def _check(rec, tag, golden=None, img_rtol=IMG_RTOL, grad_rtol=GRAD_RTOL, flip_budget=FLIP_BUDGET, floor=False):
     meta = rec["meta"]
     strict = meta["frames"] == "waves"            # untrimmed 1e-4 on every gradient
     # pose gradients are sums over the live pixels, so kink events cannot be separated: 1e-4 on the band-limited fixtures,
@@ -154,6 +183,11 @@ def _check(rec, tag, golden=None, img_rtol=IMG_RTOL, grad_rtol=GRAD_RTOL, flip_b
             assert report[f"out {k}"] <= img_rtol, f"{tag} {k}: rel-L2 {report[f'out {k}']:.3e}"
 
     # ---- gradients
+    def n_trim_of(g):
+        # K = 0.4 % of the cells on auto-masked frames; 1 % on "scene", where > 90 % of the pixels are live and every one
+        # of them can sit on a bilinear kink of its textured source frame
+        return min(max(16, g.numel() // (100 if meta["frames"] == "scene" else 250)), g.numel() // 50)
+    floors = _reference_cross_device_floor(rec, forced, ref_leaves, n_trim_of) if floor else {}
     for k, leaf in ref_leaves.items():
         g = leaf.grad
         if g is None or float(g.abs().max()) == 0.0:
@@ -166,17 +200,23 @@ def _check(rec, tag, golden=None, img_rtol=IMG_RTOL, grad_rtol=GRAD_RTOL, flip_b
                 pose_rtol = 30 * grad_rtol
             assert err <= pose_rtol, f"{tag} grad {k}: rel-L2 {err:.3e} (kink-limited bound {pose_rtol:.0e})"
         else:
-            n_trim = min(max(16, g.numel() // 250), g.numel() // 50)
+            n_trim = n_trim_of(g)
             trimmed = _trimmed_rel_l2(grads[k], g, n_trim)
             report[f"grad {k} trimmed"] = trimmed
+            if k in floors:
+                report[f"grad {k} reference-vs-reference floor"] = floors[k][0]
+                report[f"grad {k} reference-vs-reference floor trimmed"] = floors[k][1]
             if strict:
                 drop = _cells_to_drop(grads[k], g, grad_rtol)
                 report[f"grad {k} cells>tol"] = drop
                 assert drop == 0 or (drop <= event_cells and isinstance(k, tuple) and k[0] == "disp"), \
                     f"{tag} grad {k}: untrimmed rel-L2 {err:.3e}; {drop} cells (allowed {event_cells}) keep it above {grad_rtol:.0e}"
             else:
-                assert trimmed <= grad_rtol and err <= 200 * grad_rtol, \
-                    f"{tag} grad {k}: rel-L2 {err:.3e}, without the {n_trim} largest-error cells {trimmed:.3e}"
+                # where the reference run on this very GPU (eager PyTorch) is itself further than 1e-4 from its CPU run,
+                # the bound is 1.5x that cross-device floor
+                lim_t = max(grad_rtol, 1.5 * floors[k][1]) if k in floors else grad_rtol
+                assert trimmed <= lim_t and err <= 200 * grad_rtol, \
+                    f"{tag} grad {k}: rel-L2 {err:.3e}, without the {n_trim} largest-error cells {trimmed:.3e} (limit {lim_t:.2e})"
 
     # ---- the golden vectors themselves (produced by the real reference)
     if golden is not None:

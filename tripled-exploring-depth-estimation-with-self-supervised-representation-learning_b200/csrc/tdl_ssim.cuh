@@ -86,19 +86,24 @@ TDL_DEV void patch_target_stats(const float* __restrict__ ys, float2 out[kPP]) {
 }
 
 // (1 - SSIM)/2 clamped to [0,1] from the window sums of the prediction (Sx, Sxx, Sxy) and the target's (Sy, Qy, Ay);
-// Ay = Sy^2 + 81 C1
+// Ay = fl(Sy^2 + 81 C1), Qy = fl(9 Syy + fl(81 C2 - Sy^2)).
+// Two properties of the reference's arithmetic are kept by construction:
+//  * SSIM(x, x) == 0 EXACTLY (auto-masking relies on it for static scenes): numerator and denominator are evaluated
+//    by the same nest of fused multiply-adds with (Sx, Sy, Sxy) in place of (Sx, Sx, Sxx) / (Sy, Sy, Syy), so that for
+//    identical windows n1 == d1 and n2 == d2 bit for bit;
+//  * no systematic rounding offset: the constants 81 C1 / 81 C2 are only ever added to EXACT products inside an fma.
+//    Adding them to an already-rounded value of magnitude ~100 (e.g. 2 fl(Sx Sy) + K1) is off by the same fraction of
+//    an ulp for every pixel, which showed up as +1.4e-6 on the mean SSIM term (5e-5 of the loss) when first measured.
 TDL_DEV float ssim_half(float Sx, float Sxx, float Sxy, float Sy, float Qy, float Ay) {
-    const float t = Sx * Sy;
-    // (2 Sx Sy + K1 with ONE rounding: 2 fl(Sx Sy) sits on the fp32 grid of ~100, and adding the constant K1 to a grid value is
-    //  off by the same fraction of an ulp for every pixel -- a systematic 3e-8 on the SSIM term, 1e-5 of a small loss)
-    const float n1 = fmaf(2.f * Sx, Sy, kK1);
-    // (K2 is added LAST, to the small difference: -2t sits on the fp32 grid of ~40, so fl(K2 - 2t) would be off by the
-    //  same fraction of an ulp for every pixel -- a systematic +1.4e-6 on the mean SSIM term, measured)
-    const float n2 = fmaf(18.f, Sxy, -2.f * t) + kK2;
-    const float d1 = fmaf(Sx, Sx, Ay);
-    const float d2 = fmaf(-Sx, Sx, fmaf(9.f, Sxx, Qy));
-    const float n = n1 * n2, d = d1 * d2;
-    return mul_sat(d - n, 0.5f * rcp_approx(d));
+    const float n1 = fmaf(Sx, Sy, fmaf(Sx, Sy, kK1));                       // 2 Sx Sy + K1        (d1 with Sy -> Sx, Sx -> Sy)
+    const float d1 = fmaf(Sx, Sx, Ay);                                      // Sx^2 + Sy^2 + K1
+    const float qn = fmaf(9.f, Sxy, fmaf(-Sx, Sy, kK2));                    // 9 Sxy - Sx Sy + K2  (Qy with y -> x in one factor)
+    const float n2 = fmaf(-Sx, Sy, fmaf(9.f, Sxy, qn));                     // 18 Sxy - 2 Sx Sy + K2
+    const float d2 = fmaf(-Sx, Sx, fmaf(9.f, Sxx, Qy));                     // 9 Sxx - Sx^2 + 9 Syy - Sy^2 + K2
+    // (__fmul_rn / __fsub_rn: nvcc would otherwise contract d1*d2 - n into fma(d1, d2, -n), whose result for identical
+    //  windows is the rounding error of n instead of 0 -- measured as +3e-5 on the loss of a static scene)
+    const float n = __fmul_rn(n1, n2), d = __fmul_rn(d1, d2);
+    return mul_sat(__fsub_rn(d, n), 0.5f * rcp_approx(d));
 }
 
 TDL_DEV float robust_l1_fast(float x, float y) {          // sqrt((y-x)^2 + eps^2) = t * rsqrt(t)
