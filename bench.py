@@ -66,11 +66,10 @@ def parse():
     ap.add_argument("--no-train", action="store_true", help="skip the full train-step measurement")
     ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--eager-train", action="store_true", help="do not CUDA-graph the train step")
-    ap.add_argument("--train-model", default="mono_fm", choices=["mono_fm", "tripled"],
+    ap.add_argument("--train-model", default="both", choices=["both", "mono_fm", "tripled"],
                     help="mono_fm = cfg_kitti_fm (BASELINE configs[1]); tripled = cfg_kitti_tripleD (configs[2])")
-    ap.add_argument("--syncbn", action="store_true",
-                    help="convert to SyncBatchNorm like cfg_kitti_fm (syncbn = True); off by default: its ~200 tiny "
-                         "collectives per step halve 2-GPU throughput (measured: 186 vs 394 images/s)")
+    ap.add_argument("--bf16-comm", action="store_true", help="train step: all-reduce the gradients in bf16")
+    ap.add_argument("--no-channels-last", action="store_true", help="train step: keep the networks in NCHW")
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample of the cpu_baseline leg")
     ap.add_argument("--repeats", type=int, default=7, help="timed regions of --steps replays each (median is reported)")
     ap.add_argument("--no-scene", action="store_true", help="skip the representative-scene workload")
@@ -475,30 +474,26 @@ def time_cpu_arm(B, H, W, steps, warmup, kind, budget_s=None):
 
 
 # ------------------------------------------------------------------------------------------------ train step
-def train_step_bench(args, device, rank, world, dist_on):
-    """Full cfg_kitti_fm training step (config/cfg_kitti_fm.py: ResNet-50 depth net, ResNet-18 pose net, ResNet-50
-    extractor, Adam 1e-4, grad-clip 35, syncbn) with the fused loss, batch-sharded DDP over NCCL when world > 1.
-    The networks are plain PyTorch (out of the hot path's scope); reported next to the loss-only figure."""
+def train_step_bench(args, device, rank, world, dist_on, model_kind):
+    """Full training step of cfg_kitti_fm (model_kind "mono_fm": ResNet-50 depth net, ResNet-18 pose net, ResNet-50
+    extractor) or cfg_kitti_tripleD ("tripled": + in-loop encoder, image / colour decoders, erase mask) with the fused
+    loss, Adam 1e-4, grad-clip 35, batch-sharded over the ranks.  The networks are plain PyTorch / cuDNN in
+    channels_last (out of the hot path's scope); the step itself is package train_step.FlatGradStep: flat gradient
+    buffer, ONE NCCL all-reduce, fused clip, fused Adam, everything captured in one CUDA graph at every rank count.
+    Also timed in the same job: the identical step WITHOUT the collective (what one GPU alone does), which gives
+    `efficiency_vs_n1` = local step time / distributed step time."""
     tdl = importlib.import_module(PKG)
     importlib.import_module(PKG + ".nets")
+    ts = importlib.import_module(PKG + ".train_step")
     B, H, W = args.batch, args.height, args.width
     opt = opt_dict(B, H, W)
-    tripled = args.train_model == "tripled"
+    tripled = model_kind == "tripled"
     name = "mono_fm_joint_inpaint_disentangle" if tripled else "mono_fm"
     opt.update(name=name, depth_num_layers=50, pose_num_layers=18, extractor_num_layers=50,
                extractor_pretrained_path=None, dis=1e-3, cvt=1e-3, auto_res_weight=5e-3, freeze_extractor=False)
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
-    model = tdl.MONO.module_dict[name](tdl.config.ConfigDict(opt)).to(device).train()
-    n_params = sum(q.numel() for q in model.parameters() if q.requires_grad)
-    syncbn = dist_on and args.syncbn
-    if dist_on:
-        if syncbn:
-            model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index], gradient_as_bucket_view=True)
-    optim = torch.optim.Adam([q for q in model.parameters() if q.requires_grad], lr=1e-4, weight_decay=0,
-                             capturable=not dist_on and not args.eager_train, fused=None if args.no_fused_adam else True)
-    host = make_host_workload(B, H, W, rank_seed(rank))
+    host = make_host_workload(B, H, W, rank_seed(rank), "scene")
     inputs = {}
     for k, v in host.items():
         if k[0] == "in":
@@ -513,49 +508,63 @@ def train_step_bench(args, device, rank, world, dist_on):
             mask[:, :, y0:y0 + 16, x0:x0 + 16] = 0
         inputs[("mask", 0, 0)] = mask.to(device)
 
-    def step():
-        optim.zero_grad(set_to_none=True)
-        _, loss_dict = model(inputs)
-        loss = loss_dict.total()
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 35.0)
-        optim.step()
-        return loss
+    def build(world_for_step):
+        torch.manual_seed(0)
+        model = tdl.MONO.module_dict[name](tdl.config.ConfigDict(opt)).to(device).train()
+        if not args.no_channels_last:
+            model = model.to(memory_format=torch.channels_last)
+        stepper = ts.FlatGradStep(model, lr=1e-4, max_norm=35.0, world=world_for_step, bf16_comm=args.bf16_comm,
+                                  fused_adam=not args.no_fused_adam)
+        stepper.broadcast_parameters()
 
-    for _ in range(3):
-        loss = step()
-    torch.cuda.synchronize(device)
-    # The eager step is CPU-launch-bound (~1500 small kernels); capture forward + backward + clip + Adam into one
-    # CUDA graph when possible (single process; DDP's bucketed NCCL all-reduce stays eager).
-    mode = "eager"
-    run = step
-    if not dist_on and not args.eager_train:
+        def loss_fn():
+            _, loss_dict = model(inputs)
+            return loss_dict.total()
+        return model, stepper, loss_fn
+
+    def measure(world_for_step, sync_ranks):
+        model, stepper, loss_fn = build(world_for_step)
+        mode = "cuda-graph"
         try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=torch.cuda.current_stream(device)):
-                static_loss = step()
+            if args.eager_train:
+                raise RuntimeError("--eager-train")
+            stepper.capture(loss_fn, warmup=3)
+            run = stepper.replay
+        except Exception as exc:
+            if not args.eager_train:
+                print(f"train-step graph capture failed ({type(exc).__name__}: {exc}); timing the eager step", file=sys.stderr)
             torch.cuda.synchronize(device)
+            mode = "eager"
 
             def run():
-                graph.replay()
-                return static_loss
-            mode = "cuda-graph"
-            for _ in range(2):
-                loss = run()
-        except Exception as exc:                      # pragma: no cover - falls back to the eager step
-            print(f"train-step graph capture failed ({type(exc).__name__}: {exc}); timing the eager step", file=sys.stderr)
-            torch.cuda.synchronize(device)
-            run, mode = step, "eager"
-    ms = timed_region(run, args.train_steps, device, dist_on)
-    loss = run()
-    return {"images_per_s": round(whole_job_images_per_s(world, B, args.train_steps, ms), 1),
-            "ms_per_step": round(ms / args.train_steps, 3), "steps": args.train_steps, "execution": mode,
-            "model": ("TripleD mono_fm_joint_inpaint_disentangle (cfg_kitti_tripleD): ResNet-50 depth + ResNet-18 pose + "
-                      "ResNet-50 in-loop encoder + image / colour decoders, " if tripled else
-                      "mono_fm (cfg_kitti_fm): ResNet-50 depth + ResNet-18 pose + ResNet-50 extractor (level 0), ")
-                     + f"{n_params / 1e6:.1f} M trainable params, PyTorch fp32 networks + fused loss, Adam",
-            "parallelism": f"DDP x{world} (NCCL all-reduce of gradients" + (", SyncBatchNorm)" if syncbn else ")"),
-            "final_loss": float(loss.detach())}
+                return stepper.step(loss_fn)
+        for _ in range(3):
+            loss = run()
+        ms = timed_region(run, args.train_steps, device, sync_ranks)
+        loss = run()
+        out = (ms / args.train_steps, mode, float(loss.detach()), stepper.n_params())
+        del model, stepper
+        torch.cuda.empty_cache()
+        return out
+
+    ms_step, mode, final_loss, n_params = measure(world, dist_on)
+    local_ms = None
+    if dist_on:
+        local_ms, _, _, _ = measure(1, dist_on)       # the same step without the collective, on every rank at the same time
+    res = {"images_per_s": round(world * B / (ms_step * 1e-3), 1), "ms_per_step": round(ms_step, 3), "steps": args.train_steps,
+           "execution": mode, "data": "scene",
+           "model": ("TripleD mono_fm_joint_inpaint_disentangle (cfg_kitti_tripleD): ResNet-50 depth + ResNet-18 pose + "
+                     "ResNet-50 in-loop encoder + image / colour decoders, " if tripled else
+                     "mono_fm (cfg_kitti_fm): ResNet-50 depth + ResNet-18 pose + ResNet-50 extractor (level 0), ")
+                    + f"{n_params / 1e6:.1f} M trainable params, PyTorch fp32 networks"
+                    + ("" if args.no_channels_last else " (channels_last)") + " + fused loss, fused clip + Adam",
+           "parallelism": f"batch-sharded x{world}: one flat NCCL all-reduce of {n_params * (2 if args.bf16_comm else 4) / 1e6:.0f} MB "
+                          f"({'bf16' if args.bf16_comm else 'fp32'}) per step inside the graph, per-rank BatchNorm",
+           "final_loss": final_loss}
+    if local_ms is not None:
+        res["local_ms_per_step"] = round(local_ms, 3)
+        res["efficiency_vs_n1"] = round(local_ms / ms_step, 4)
+    return res
 
 
 def time_eager_gpu_port(B, H, W, device, steps=5, warmup=2):
@@ -705,10 +714,13 @@ def run():
     io_bytes = io_a.h2d_bytes()
     del io_a, io_b
 
-    train = None
+    train = train_tripled = None
     if not args.no_train:
         torch.cuda.empty_cache()
-        train = train_step_bench(args, device, rank, world, dist_on)
+        if args.train_model in ("both", "mono_fm"):
+            train = train_step_bench(args, device, rank, world, dist_on, "mono_fm")
+        if args.train_model in ("both", "tripled"):
+            train_tripled = train_step_bench(args, device, rank, world, dist_on, "tripled")
 
     if rank != 0:
         if dist_on:
@@ -798,7 +810,7 @@ def run():
             "gpu_launches_per_step": smooth["launches_per_step"],
             "smooth": block(smooth, k_smooth), "scene": block(scene, dom_tab) if scene else None,
             "roofline": roofline, "cpu_baseline": cpu, "eager_torch_gpu_baseline": eager,
-            "train_step": train}
+            "train_step": train, "train_step_tripled": train_tripled}
     if dist_on:
         torch.distributed.destroy_process_group()
     return line
