@@ -73,6 +73,10 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample of the cpu_baseline leg")
     ap.add_argument("--repeats", type=int, default=7, help="timed regions of --steps replays each (median is reported)")
     ap.add_argument("--no-scene", action="store_true", help="skip the representative-scene workload")
+    ap.add_argument("--feat-layout", default="nhwc", choices=["nhwc", "nchw"],
+                    help="memory layout of the 64-channel feature maps handed to the loss: nhwc = torch channels_last, what the "
+                         "cuDNN extractor produces on B200 (default); nchw = the reference's contiguous layout")
+    ap.add_argument("--no-bf16", action="store_true", help="skip the opt-in bf16-storage measurement of the scene workload")
     ap.add_argument("--ref-budget-s", type=float, default=240.0,
                     help="--impl reference: wall-clock budget; the per-step sample (batch) is halved until the run fits")
     ap.add_argument("--no-fused-adam", action="store_true",
@@ -169,13 +173,25 @@ def make_host_workload(B, H, W, seed, frames="smooth"):
     return host
 
 
+FEAT_LAYOUT = "nhwc"
+FEAT_DTYPE = torch.float32
+
+
+def _is_feat_key(k):
+    return k[0] == "leaf" and (k[1] == "tgt_feat" or (isinstance(k[1], tuple) and k[1][0] == "src_feat"))
+
+
 class DeviceStep:
     """The loss step on static device buffers: eager, or captured once into a CUDA graph and replayed."""
 
-    def __init__(self, host, B, H, W, device, trainable_feat):
+    def __init__(self, host, B, H, W, device, trainable_feat, feat_dtype=None):
         tdl = importlib.import_module(PKG)
         self.tdl, self.device = tdl, device
-        self.buf = {k: v.to(device).contiguous() for k, v in host.items()}
+        feat_dtype = feat_dtype or FEAT_DTYPE
+        if FEAT_LAYOUT == "nhwc" or feat_dtype != torch.float32:   # host buffers already in the layout / dtype the device wants
+            host = {k: (v.to(feat_dtype).contiguous(memory_format=torch.channels_last) if _is_feat_key(k) else v)
+                    for k, v in host.items()}
+        self.buf = {k: (v.to(device) if _is_feat_key(k) else v.to(device).contiguous()) for k, v in host.items()}
         self.host = {k: v.pin_memory() for k, v in host.items()}
         self.trainable_feat = trainable_feat
         self.grad_keys = [k for k in self.buf if k[0] == "leaf" and
@@ -282,14 +298,14 @@ def timed_region(fn, steps, device, dist_on, warm=None):
     return max_over_ranks(a.elapsed_time(b), device, dist_on)
 
 
-def measure_workload(frames, args, device, rank, world, dist_on, trainable):
+def measure_workload(frames, args, device, rank, world, dist_on, trainable, feat_dtype=None):
     """Per-kernel device times (eager, CUDA events inside the library) and the graph-replay step time of one workload:
     `repeats` timed regions of exactly args.steps replays, each bracketed by barrier + synchronize, max over ranks;
     the median region is the reported figure."""
     tdl = importlib.import_module(PKG)
     B, H, W = args.batch, args.height, args.width
     host = make_host_workload(B, H, W, rank_seed(rank), frames)
-    step = DeviceStep(host, B, H, W, device, trainable)
+    step = DeviceStep(host, B, H, W, device, trainable, feat_dtype)
     for _ in range(3):
         step.run_eager()
     torch.cuda.synchronize(device)
@@ -356,7 +372,10 @@ class ImagesOnlyStep(DeviceStep):
         self.frames_dev = {f: torch.empty_like(v, device=device) for f, v in self.frames_u8.items()}
         self.host = {k: v for k, v in self.host.items() if k[0] == "in" and not isinstance(k[1], tuple)}   # K, inv_K
         g = torch.Generator().manual_seed(0)
-        self.stem = (torch.randn(FEAT_C, 3, 7, 7, generator=g) * 0.1).to(device).requires_grad_(True)
+        self.stem = (torch.randn(FEAT_C, 3, 7, 7, generator=g) * 0.1).to(device)
+        if FEAT_LAYOUT == "nhwc":
+            self.stem = self.stem.contiguous(memory_format=torch.channels_last)
+        self.stem.requires_grad_(True)
 
     def _step(self):
         b = self.buf
@@ -364,11 +383,12 @@ class ImagesOnlyStep(DeviceStep):
             b[k].grad = None
         self.stem.grad = None
         imgs = {f: self.frames_dev[f].float() * (1.0 / 255.0) for f in FRAME_IDS}
+        conv_in = {f: (v.contiguous(memory_format=torch.channels_last) if FEAT_LAYOUT == "nhwc" else v) for f, v in imgs.items()}
         inputs = {k[1]: v for k, v in b.items() if k[0] == "in" and not isinstance(k[1], tuple)}
         for f in FRAME_IDS:
             inputs[("color", f, 0)] = imgs[f]
         outputs = {k[1]: v for k, v in b.items() if k[0] == "leaf"}
-        feats = {f: torch.relu(torch.nn.functional.conv2d(imgs[f], self.stem, stride=2, padding=3)) for f in FRAME_IDS}
+        feats = {f: torch.relu(torch.nn.functional.conv2d(conv_in[f], self.stem, stride=2, padding=3)) for f in FRAME_IDS}
         loss_dict = self.net.compute_losses_fm(inputs, outputs, None, feats[0], {f: feats[f] for f in FRAME_IDS[1:]})
         total = loss_dict.total()
         total.backward()
@@ -601,7 +621,7 @@ def time_eager_gpu_port(B, H, W, device, steps=5, warmup=2):
 def config_dict(args, trainable):
     return {"workload": f"mono_fm loss fwd+bwd (cfg_kitti_fm): {args.height}x{args.width}, batch {args.batch}/GPU, "
                         f"frames [0,-1,1], 4 scales, {FEAT_C}-ch features at H/2xW/2, "
-                        f"{'trainable' if trainable else 'frozen'} extractor features, reference-faithful outputs "
+                        f"{'trainable' if trainable else 'frozen'} extractor features in {FEAT_LAYOUT.upper()} memory, reference-faithful outputs "
                         "(warped images/features + int64 min_index materialised), in-kernel Philox automask noise; "
                         "value = 'smooth' synthetic frames (SURVEY 8d), `scene` block = rendered moving-camera frames",
             "global_batch": args.batch * args.gpus, "per_gpu_batch": args.batch,
@@ -635,9 +655,10 @@ def main():
 
 
 def run():
-    global SEED_OFFSET
+    global SEED_OFFSET, FEAT_LAYOUT
     args = parse()
     SEED_OFFSET = args.seed_offset
+    FEAT_LAYOUT = args.feat_layout
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -686,6 +707,11 @@ def run():
     smooth = measure_workload("smooth", args, device, rank, world, dist_on, trainable)
     scene = None if args.no_scene else measure_workload("scene", args, device, rank, world, dist_on, trainable)
     clocks = sampler.stop() if rank == 0 else None
+    # opt-in storage mode (north_star "bf16/fp32 loads"): feature maps stored bf16, fp32 arithmetic; never the parity config
+    scene_bf16 = None
+    if not (args.no_scene or args.no_bf16):
+        scene_bf16 = measure_workload("scene", args, device, rank, world, dist_on, trainable, torch.bfloat16)
+        del scene_bf16["step"], scene_bf16["host"]
     step, host = smooth["step"], smooth["host"]
     ms_step = smooth["ms_per_step"]
     value = world * B / (ms_step * 1e-3)
@@ -737,7 +763,11 @@ def run():
     alg = algorithmic_bytes(B, H, W, S, FEAT_C, len(SCALES), trainable)
     total_alg = sum(alg[k] for k in ("photo_fwd", "photo_bwd", "feat_fwd", "feat_bwd", "memset_dsrc"))
 
-    def kernel_table(m):
+    alg_bf16 = dict(alg)
+    for k in ("feat_fwd", "feat_bwd", "memset_dsrc"):
+        alg_bf16[k] = alg[k] // 2
+
+    def kernel_table(m, alg=alg):
         kernels = {}
         for name, (n, total_ms) in m["kern"].items():
             avg_us = total_ms / n * 1e3
@@ -809,6 +839,11 @@ def run():
             "gpu_launches": smooth["launches_per_step"] * args.steps * smooth["repeats"]["n"],
             "gpu_launches_per_step": smooth["launches_per_step"],
             "smooth": block(smooth, k_smooth), "scene": block(scene, dom_tab) if scene else None,
+            "scene_bf16_features": (dict(block(scene_bf16, kernel_table(scene_bf16, alg_bf16)),
+                                         what="opt-in: 64-channel feature maps stored in bf16 (half the feature bytes), fp32 arithmetic; "
+                                              "images, disparities and every loss / gradient of them stay fp32",
+                                         alg_bytes=sum(alg_bf16[k] for k in ("photo_fwd", "photo_bwd", "feat_fwd", "feat_bwd", "memset_dsrc")))
+                                    if scene_bf16 else None),
             "roofline": roofline, "cpu_baseline": cpu, "eager_torch_gpu_baseline": eager,
             "train_step": train, "train_step_tripled": train_tripled}
     if dist_on:

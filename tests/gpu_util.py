@@ -29,13 +29,24 @@ def rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
+FEAT_LAYOUT = "nchw"      # "nhwc": hand the feature maps over in channels_last memory (tests/test_gpu_feat_nhwc.py)
+
+
+def _leaf(k, v, dev):
+    v = v.to(dev).clone()
+    is_feat = k == "tgt_feat" or (isinstance(k, tuple) and k[0] == "src_feat")
+    if is_feat and FEAT_LAYOUT == "nhwc":
+        v = v.contiguous(memory_format=torch.channels_last)
+    return v.requires_grad_(True)
+
+
 def run_cuda(rec, noise, dev="cuda", kind=None):
     """rec: golden record (or same layout); noise[s][f] CPU tensors.  Returns loss_dict, outputs, grads."""
     meta = rec["meta"]
     kind = kind or meta["kind"]
     net = make_loss_net(meta["opt"], kind)
     inputs = {k: v.to(dev) for k, v in rec["inputs"].items()}
-    leaves = {k: v.to(dev).clone().requires_grad_(True) for k, v in rec["leaves"].items()}
+    leaves = {k: _leaf(k, v, dev) for k, v in rec["leaves"].items()}
     outputs = {k: v for k, v in leaves.items()
                if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam", "res_img", "auto_res_img")}
     noise_d = {s: {f: n.to(dev) for f, n in d.items()} for s, d in noise.items()}

@@ -414,7 +414,12 @@ static int check_feat(const tdl_feat_args* a, bool bwd, FeatDev* d) {
     d->min_disp = (float)(1.0 / a->max_depth);
     d->range = (float)(1.0 / a->min_depth - 1.0 / a->max_depth);
     d->coef = a->coef;
-    if (a->layout != TDL_LAYOUT_NCHW || a->dtype != TDL_DTYPE_F32) return TDL_ERR_SHAPE;
+    if (a->layout != TDL_LAYOUT_NCHW && a->layout != TDL_LAYOUT_NHWC) return TDL_ERR_SHAPE;
+    if (a->dtype != TDL_DTYPE_F32 && a->dtype != TDL_DTYPE_BF16) return TDL_ERR_SHAPE;
+    if (a->dtype == TDL_DTYPE_BF16 && a->layout != TDL_LAYOUT_NHWC) return TDL_ERR_SHAPE;          // bf16 rows only
+    if (a->layout == TDL_LAYOUT_NHWC && a->C % 4 != 0) return TDL_ERR_COUNT;
+    d->layout = a->layout;
+    d->dtype = a->dtype;
     d->tgt = static_cast<const float*>(a->tgt); d->disp = a->disp; d->P = a->P; d->invK = a->invK;
     int n_dsrc = 0;
     for (int f = 0; f < a->S; ++f) {
@@ -434,8 +439,10 @@ static int check_feat(const tdl_feat_args* a, bool bwd, FeatDev* d) {
         if (!a->dloss || !a->d_disp || !a->dP) return TDL_ERR_NULL;
         d->dloss = a->dloss; d->d_tgt = static_cast<float*>(a->d_tgt); d->d_disp = a->d_disp; d->dP = a->dP;
         const FeatScratchLayout L = feat_scratch_layout(a->B, a->C, a->h, a->w, a->S);
-        if (n_dsrc == a->S && a->bwd_scratch && a->bwd_scratch_bytes >= L.total && a->C % 4 == 0 && (uint64_t)a->h * a->w * a->C < (1ull << 28) &&
-            (reinterpret_cast<uintptr_t>(a->bwd_scratch) & 15) == 0 && !opt(kOptFeatAtomic)) {
+        const bool scratch_ok = a->bwd_scratch && a->bwd_scratch_bytes >= L.total && (reinterpret_cast<uintptr_t>(a->bwd_scratch) & 15) == 0;
+        if (a->layout == TDL_LAYOUT_NHWC && n_dsrc == a->S && !scratch_ok) return TDL_ERR_WORKSPACE;   // no atomic fallback for rows
+        if (n_dsrc == a->S && scratch_ok && a->C % 4 == 0 && (uint64_t)a->h * a->w * a->C < (1ull << 28) &&
+            (a->layout == TDL_LAYOUT_NHWC || !opt(kOptFeatAtomic))) {
             char* sc = static_cast<char*>(a->bwd_scratch);
             d->ov_cnt = reinterpret_cast<int*>(sc + L.cnt_off);
             d->dP_acc = reinterpret_cast<float*>(sc + L.cnt_off + align_up((uint64_t)feat_chunk_images(a->B, a->C, a->h, a->w) * sizeof(int), 256));
@@ -455,7 +462,7 @@ int tdl_feat_fwd(const tdl_feat_args* a, tdl_stream_t stream) {
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("memset", cudaMemsetAsync(d.acc, 0, (size_t)a->B * sizeof(double), st));
-    TDL_KERNEL("feat_fwd", launch_feat_fwd(d, st));
+    TDL_KERNEL("feat_fwd", d.layout == TDL_LAYOUT_NHWC ? launch_feat_fwd_nhwc(d, st) : launch_feat_fwd(d, st));
     TDL_KERNEL("feat_finalize", launch_feat_finalize(d, st));
     return TDL_OK;
 }
@@ -466,7 +473,13 @@ int tdl_feat_bwd(const tdl_feat_args* a, tdl_stream_t stream) {
     if (rc == TDL_OK) rc = check_device();
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t fbytes = (size_t)a->B * a->C * a->h * a->w * sizeof(float);
+    const size_t esz = a->dtype == TDL_DTYPE_BF16 ? 2 : sizeof(float);
+    const size_t fbytes = (size_t)a->B * a->C * a->h * a->w * esz;
+    const bool nhwc = a->layout == TDL_LAYOUT_NHWC;
+    // per-image offset of a feature tensor, in units of the float* the descriptors carry (bf16 images are half as long)
+    auto feat_off = [&](const float* base, size_t b0, size_t img) {
+        return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + b0 * img * esz);
+    };
     if (!d.G)        // (bucketed path: dP is accumulated in the zeroed scratch header and written by the gather kernel)
         TDL_KERNEL("memset", cudaMemsetAsync(a->dP, 0, (size_t)a->B * a->S * 12 * sizeof(float), st));
     if (a->disp_h != a->h || a->disp_w != a->w)
@@ -478,23 +491,27 @@ int tdl_feat_bwd(const tdl_feat_args* a, tdl_stream_t stream) {
         for (int b0 = 0; b0 < a->B; b0 += Bc) {
             FeatDev c = d;                                    // this chunk's view of every per-image tensor
             c.B = a->B - b0 < Bc ? a->B - b0 : Bc;
-            c.tgt += b0 * img;
+            c.tgt = feat_off(d.tgt, b0, img);
             c.disp += (size_t)b0 * a->disp_h * a->disp_w;
             c.P += (size_t)b0 * a->S * 12;
             c.invK += (size_t)b0 * 9;
             c.argmin += (size_t)b0 * a->h * a->w;
-            if (c.d_tgt) c.d_tgt += b0 * img;
+            if (c.d_tgt) c.d_tgt = const_cast<float*>(feat_off(d.d_tgt, b0, img));
             c.d_disp += (size_t)b0 * a->disp_h * a->disp_w;
             c.dP += (size_t)b0 * a->S * 12;
             for (int f = 0; f < a->S; ++f) {
-                c.src[f] += b0 * img;
-                c.d_src[f] += b0 * img;
+                c.src[f] = feat_off(d.src[f], b0, img);
+                c.d_src[f] = const_cast<float*>(feat_off(d.d_src[f], b0, img));
             }
             TDL_KERNEL("memset", cudaMemsetAsync(c.ov_cnt, 0, L.cnt_bytes, st));
-            TDL_KERNEL("feat_bwd", launch_feat_bwd(c, st));
-            TDL_KERNEL("feat_gather", launch_feat_bwd_gather(c, st));
-            TDL_KERNEL("feat_overflow", launch_feat_bwd_overflow(c, st));
+            TDL_KERNEL("feat_bwd", nhwc ? launch_feat_bwd_nhwc(c, st) : launch_feat_bwd(c, st));
+            TDL_KERNEL("feat_gather", nhwc ? launch_feat_gather_nhwc(c, st) : launch_feat_bwd_gather(c, st));
+            TDL_KERNEL("feat_overflow", nhwc ? launch_feat_overflow_nhwc(c, st) : launch_feat_bwd_overflow(c, st));
         }
+        return TDL_OK;
+    }
+    if (nhwc) {                                       // frozen extractor: no d_src (checked above), d_tgt optional
+        TDL_KERNEL("feat_bwd", launch_feat_bwd_nhwc(d, st));
         return TDL_OK;
     }
     for (int f = 0; f < a->S; ++f)

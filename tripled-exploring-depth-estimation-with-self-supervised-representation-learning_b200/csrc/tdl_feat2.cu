@@ -1,0 +1,542 @@
+// Feature-metric (FeatDepth) loss on CHANNEL-LAST feature maps, forward and backward (sm_100a).
+//
+//   generate_features_pred + compute_perceptional_loss + min over source frames
+//   mono/model/mono_fm/net.py:59-61,111-118,172-199; mono/model/mono_fm_joint_inpaint/net.py:58-70
+//
+// Layout TDL_LAYOUT_NHWC: (B, h, w, C) contiguous -- the memory of a torch channels_last (B, C, h, w) tensor, which is
+// what cuDNN produces on B200 when the extractor runs in channels_last.  One bilinear tap is then ONE contiguous row of
+// C values (256 bytes at C = 64 fp32, 128 bytes in bf16) instead of C scattered 4-byte loads C*h*w*4 bytes apart: the
+// NCHW kernels of tdl_feat.cu are bound by L1/TEX wavefronts (67-85 %, ncu) for exactly that reason.
+// Storage TDL_DTYPE_BF16 (opt-in): rows are read / written as bf16, every product and sum is fp32 in registers.
+//
+// Thread mapping (all three kernels): a warp owns 32 consecutive pixels.  Phase 1, lane = pixel: projection, taps,
+// bucket registration -- scalar per-pixel work, parked in shared memory.  Phase 2, two pixels at a time: each half-warp
+// takes one pixel, lane l of the half owns channels 4l .. 4l+3 of a 64-channel chunk (one 16-byte / 8-byte access per row).
+#include "tdl_common.cuh"
+#include "tdl_internal.h"
+
+#include <cuda_bf16.h>
+
+namespace tdl {
+
+namespace f2 {
+constexpr int NT = 128;                 // 4 warps
+constexpr int PIX = 32;                 // pixels per warp
+
+template <typename T>
+TDL_DEV float4 ld4(const T* p);
+template <>
+TDL_DEV float4 ld4<float>(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <>
+TDL_DEV float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    // bf16 -> fp32 is a 16-bit shift
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+}
+template <typename T>
+TDL_DEV void st4(T* p, float4 v);
+template <>
+TDL_DEV void st4<float>(float* p, float4 v) {
+    *reinterpret_cast<float4*>(p) = v;
+}
+template <>
+TDL_DEV void st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const unsigned*>(&a);
+    u.y = *reinterpret_cast<const unsigned*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+struct Tap {                            // one pixel, one source frame: north-west corner + the four bilinear weights
+    int o00;                            // y0 * w + x0; bit 30: east column inside, bit 29: south row inside
+    float nw, ne, sw, se;
+};
+}  // namespace f2
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int S, typename T>
+__global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) {
+    using namespace f2;
+    __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
+    __shared__ Tap s_tap[NT / 32][PIX][S];
+    __shared__ float s_res[NT / 32][PIX][S];
+    __shared__ float s_red[32];
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5, half = lane >> 4, l16 = lane & 15;
+    const int b = blockIdx.y;
+    const int h = p.h, w = p.w, C = p.C;
+    const int hw = h * w;
+    if (tid < S * 12) s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
+    if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
+    __syncthreads();
+    const int pix0 = (blockIdx.x * (NT / 32) + wq) * PIX;
+    // ---- phase 1: lane = pixel
+    {
+        const int pix = min(pix0 + lane, hw - 1);
+        const int y = pix / w, x = pix - y * w;
+        const DepthParams dp{p.min_disp, p.range};
+        const UpTap ut = up_tap(y, x, p.sy, p.sx, p.dh, p.dw);
+        const Geo g = backproject(up_value(p.disp + (size_t)b * p.dh * p.dw, p.dw, ut), dp, s_cam + TDL_MAX_SRC * 12, x, y);
+        const ProjConst pc = make_proj_const(h, w, p.align_corners);
+#pragma unroll
+        for (int f = 0; f < S; ++f) {
+            const Proj pr = project<false>(g, s_cam + f * 12, pc);
+            const Bilin bt = bilin_taps(pr.ix, pr.iy, h, w);
+            s_tap[wq][lane][f] = Tap{(bt.y0 * w + bt.x0) | (bt.vx ? (1 << 30) : 0) | (bt.vy ? (1 << 29) : 0), bt.nw, bt.ne, bt.sw, bt.se};
+        }
+    }
+    __syncwarp();
+    // ---- phase 2: two pixels per step, one half-warp each.  Every row of a pixel (target + 4 taps per source frame) is
+    //      requested before the first use, and the rows of the NEXT pixel are requested before the arithmetic of the current
+    //      one (the stores of the warped rows would otherwise fence the loads: the pointers may alias for the compiler)
+    const T* __restrict__ tgt = reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C;
+    const T* __restrict__ srcb[S];
+    T* __restrict__ wrpb[S];
+#pragma unroll
+    for (int f = 0; f < S; ++f) {
+        srcb[f] = reinterpret_cast<const T*>(p.src[f]) + (size_t)b * hw * C;
+        wrpb[f] = p.warped[f] ? reinterpret_cast<T*>(p.warped[f]) + (size_t)b * hw * C : nullptr;
+    }
+    struct Rows {
+        float4 t, v[S][4];
+        float wgt[S][4];
+    };
+    auto fetch = [&](int pl, int c, Rows& r) {
+        const int pix = min(pix0 + pl, hw - 1);
+        r.t = ld4(tgt + (size_t)pix * C + c);
+#pragma unroll
+        for (int f = 0; f < S; ++f) {
+            const Tap tp = s_tap[wq][pl][f];
+            const int o = tp.o00 & 0x1fffffff;
+            const int dx = (tp.o00 >> 30) & 1, dy = ((tp.o00 >> 29) & 1) ? w : 0;
+            // a clamped tap has weight exactly 0, so loading the clamped row adds 0 like ATen's skipped tap
+            const T* sb = srcb[f] + c;
+            r.v[f][0] = ld4(sb + (size_t)o * C);
+            r.v[f][1] = ld4(sb + (size_t)(o + dx) * C);
+            r.v[f][2] = ld4(sb + (size_t)(o + dy) * C);
+            r.v[f][3] = ld4(sb + (size_t)(o + dy + dx) * C);
+            r.wgt[f][0] = tp.nw;
+            r.wgt[f][1] = tp.ne;
+            r.wgt[f][2] = tp.sw;
+            r.wgt[f][3] = tp.se;
+        }
+    };
+    const int nchunk = (C + 63) / 64;                       // 64-channel chunks; lanes past C idle in the last one
+    const int nsteps = (PIX / 2) * nchunk;
+    const int cl = 4 * l16;
+    float acc[S];
+#pragma unroll
+    for (int f = 0; f < S; ++f) acc[f] = 0.f;
+    // one step: request the rows of step it+1 into `nxt`, then consume `cur` (requested one step earlier).  Two register
+    // sets alternate (no copy between them: a copy would wait for the loads it is meant to overlap)
+    auto step = [&](int it, Rows& cur, Rows& nxt) {
+        const int q = (it / nchunk) * 2, ck = it - (it / nchunk) * nchunk;
+        const int pl = q + half, c = cl + 64 * ck;
+        const int pix = pix0 + pl;
+        if (it + 1 < nsteps) {
+            const int q2 = ((it + 1) / nchunk) * 2, ck2 = (it + 1) - ((it + 1) / nchunk) * nchunk;
+            fetch(q2 + half, min(cl + 64 * ck2, C - 4), nxt);
+        }
+        if (pix < hw && c < C) {
+#pragma unroll
+            for (int f = 0; f < S; ++f) {
+                float4 v;
+                v.x = cur.v[f][0].x * cur.wgt[f][0] + cur.v[f][1].x * cur.wgt[f][1] + cur.v[f][2].x * cur.wgt[f][2] + cur.v[f][3].x * cur.wgt[f][3];
+                v.y = cur.v[f][0].y * cur.wgt[f][0] + cur.v[f][1].y * cur.wgt[f][1] + cur.v[f][2].y * cur.wgt[f][2] + cur.v[f][3].y * cur.wgt[f][3];
+                v.z = cur.v[f][0].z * cur.wgt[f][0] + cur.v[f][1].z * cur.wgt[f][1] + cur.v[f][2].z * cur.wgt[f][2] + cur.v[f][3].z * cur.wgt[f][3];
+                v.w = cur.v[f][0].w * cur.wgt[f][0] + cur.v[f][1].w * cur.wgt[f][1] + cur.v[f][2].w * cur.wgt[f][2] + cur.v[f][3].w * cur.wgt[f][3];
+                if (wrpb[f]) st4(wrpb[f] + (size_t)pix * C + c, v);
+                const float e0 = v.x - cur.t.x, e1 = v.y - cur.t.y, e2 = v.z - cur.t.z, e3 = v.w - cur.t.w;      // robust_l1(tgt_f, src_f)
+                acc[f] += sqrt_fast(fmaf(e0, e0, kL1Eps2)) + sqrt_fast(fmaf(e1, e1, kL1Eps2)) +
+                          sqrt_fast(fmaf(e2, e2, kL1Eps2)) + sqrt_fast(fmaf(e3, e3, kL1Eps2));
+            }
+        }
+        if (ck == nchunk - 1) {                              // last chunk of this pixel pair: reduce over the 16 lanes
+#pragma unroll
+            for (int f = 0; f < S; ++f) {
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], o);
+                if (l16 == 0) s_res[wq][pl][f] = acc[f];
+                acc[f] = 0.f;
+            }
+        }
+    };
+    {
+        Rows ra, rb;
+        fetch(half, min(cl, C - 4), ra);
+        for (int it = 0; it < nsteps; it += 2) {             // nsteps is even (PIX / 2 = 16 pixel pairs)
+            step(it, ra, rb);
+            step(it + 1, rb, ra);
+        }
+    }
+    __syncwarp();
+    // ---- lane = pixel again: minimum over the source frames
+    float best = 0.f;
+    {
+        const int pix = pix0 + lane;
+        if (pix < hw) {
+            const float fc = (float)C;
+            int arg = 0;
+            best = __fdiv_rn(s_res[wq][lane][0], fc);
+#pragma unroll
+            for (int f = 1; f < S; ++f) {
+                const float v = __fdiv_rn(s_res[wq][lane][f], fc);
+                if (v < best) {
+                    best = v;
+                    arg = f;
+                }
+            }
+            p.argmin[(size_t)b * hw + pix] = (unsigned char)arg;
+            if (p.min_index) p.min_index[(size_t)b * hw + pix] = arg;
+        }
+    }
+    best = block_sum(best, s_red);
+    if (tid == 0) atomicAdd(p.acc + b, (double)best);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward, per-pixel part: only the arg-min source of each pixel receives gradient (torch.min backward).
+// Writes d_tgt (= -g, one row per pixel), g itself into G when d_tgt is not requested, d_disp, dP, and -- kGrad --
+// registers the (up to) four taps of the pixel in the bucket of the SOURCE pixel they touch (see tdl_feat.cu).
+template <bool kGrad, typename T>
+__global__ void __launch_bounds__(f2::NT) feat_bwd_nhwc_kernel(const FeatDev p) {
+    using namespace f2;
+    __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
+    __shared__ float s_dP[TDL_MAX_SRC * 12];
+    __shared__ Tap s_tap[NT / 32][PIX];
+    __shared__ int s_fs[NT / 32][PIX];
+    __shared__ float2 s_gxy[NT / 32][PIX];           // d loss / d (ix, iy) of the pixel, before the clip mask
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5, half = lane >> 4, l16 = lane & 15;
+    const int b = blockIdx.y;
+    const int h = p.h, w = p.w, C = p.C, S = p.S;
+    const int hw = h * w;
+    if (tid < S * 12) {
+        s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
+        s_dP[tid] = 0.f;
+    }
+    if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
+    __syncthreads();
+    const int pix0 = (blockIdx.x * (NT / 32) + wq) * PIX;
+    const DepthParams dp{p.min_disp, p.range};
+    const ProjConst pc = make_proj_const(h, w, p.align_corners);
+    // ---- phase 1: lane = pixel
+    const int mypix = pix0 + lane;
+    const bool active = mypix < hw;
+    const int pixc = active ? mypix : hw - 1;
+    const int y = pixc / w, x = pixc - y * w;
+    const int fsel = active ? p.argmin[(size_t)b * hw + pixc] : 0;
+    const UpTap ut = up_tap(y, x, p.sy, p.sx, p.dh, p.dw);
+    const Geo g = backproject(up_value(p.disp + (size_t)b * p.dh * p.dw, p.dw, ut), dp, s_cam + TDL_MAX_SRC * 12, x, y);
+    const float* Pf = s_cam + fsel * 12;
+    const Proj pr = project<true>(g, Pf, pc);
+    const Bilin bt = bilin_taps(pr.ix, pr.iy, h, w);
+    const int o00 = bt.y0 * w + bt.x0;
+    s_tap[wq][lane] = Tap{o00 | (bt.vx ? (1 << 30) : 0) | (bt.vy ? (1 << 29) : 0), bt.nw, bt.ne, bt.sw, bt.se};
+    s_fs[wq][lane] = fsel;
+    if (kGrad && active) {                                   // register the taps (channel independent)
+        const int fb = fsel * p.B + b;
+        int* cnt = p.bk_cnt + (size_t)fb * hw;
+        int2* ent = p.bk_ent + (size_t)fb * hw * kFeatBucketCap;
+        auto reg = [&](int o, float wgt) {
+            if (wgt != 0.f) {                                // a zero weight contributes exactly 0
+                const int slot = atomicAdd(cnt + o, 1);
+                if (slot < kFeatBucketCap) {
+                    ent[(size_t)o * kFeatBucketCap + slot] = make_int2(mypix, __float_as_int(wgt));
+                } else {
+                    const int k = atomicAdd(p.ov_cnt + b, 1);
+                    p.ov_ent[(size_t)b * 4 * hw + k] = make_int4(fsel, o, mypix, __float_as_int(wgt));
+                }
+            }
+        };
+        reg(o00, bt.nw);
+        if (bt.vx) reg(o00 + 1, bt.ne);
+        if (bt.vy) reg(o00 + w, bt.sw);
+        if (bt.vx && bt.vy) reg(o00 + w + 1, bt.se);
+    }
+    __syncwarp();
+    // ---- phase 2: two pixels per step
+    const float up = __ldg(p.dloss) * p.coef / ((float)p.Bnorm * (float)h * (float)w) / (float)C;
+    const T* __restrict__ tgt = reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C;
+    T* __restrict__ dtg = p.d_tgt ? reinterpret_cast<T*>(p.d_tgt) + (size_t)b * hw * C : nullptr;
+    T* Gb = (kGrad && !p.d_tgt) ? reinterpret_cast<T*>(p.G) + (size_t)b * hw * C : nullptr;
+    // the five rows of a pixel (target + 4 taps of its arg-min frame) are requested one step ahead of the arithmetic
+    struct Rows {
+        float4 t, a, bq, cq, d;
+    };
+    auto fetch = [&](int pl, int c, Rows& r) {
+        const int pix = min(pix0 + pl, hw - 1);
+        const Tap tp = s_tap[wq][pl];
+        const int fs = s_fs[wq][pl];
+        const float* sbf = p.src[0];
+#pragma unroll
+        for (int f = 1; f < TDL_MAX_SRC; ++f)
+            if (f == fs) sbf = p.src[f];
+        const T* sb = reinterpret_cast<const T*>(sbf) + (size_t)b * hw * C + c;
+        const int o = tp.o00 & 0x1fffffff;
+        const int dx = (tp.o00 >> 30) & 1, dy = ((tp.o00 >> 29) & 1) ? w : 0;
+        r.t = ld4(tgt + (size_t)pix * C + c);
+        r.a = ld4(sb + (size_t)o * C);
+        r.bq = ld4(sb + (size_t)(o + dx) * C);
+        r.cq = ld4(sb + (size_t)(o + dy) * C);
+        r.d = ld4(sb + (size_t)(o + dy + dx) * C);
+    };
+    const int nchunk = (C + 63) / 64;
+    const int nsteps = (PIX / 2) * nchunk;
+    const int cl = 4 * l16;
+    float gix = 0.f, giy = 0.f;
+    auto step = [&](int it, Rows& cur, Rows& nxt) {           // two register sets alternate, see feat_fwd_nhwc_kernel
+        const int q = (it / nchunk) * 2, ck = it - (it / nchunk) * nchunk;
+        const int pl = q + half, c = cl + 64 * ck;
+        const int pix = pix0 + pl;
+        if (it + 1 < nsteps) {
+            const int q2 = ((it + 1) / nchunk) * 2, ck2 = (it + 1) - ((it + 1) / nchunk) * nchunk;
+            fetch(q2 + half, min(cl + 64 * ck2, C - 4), nxt);
+        }
+        if (pix < hw && c < C) {
+            const Tap tp = s_tap[wq][pl];
+            const bool vx = (tp.o00 >> 30) & 1, vy = (tp.o00 >> 29) & 1;
+            // weights back to the fractions: nw = ex*ey, ne = ax*ey, sw = ex*ay, se = ax*ay with ex + ax = ey + ay = 1
+            const float ax = tp.ne + tp.se, ay = tp.sw + tp.se, ex = tp.nw + tp.sw, ey = tp.nw + tp.ne;
+            float4 a = cur.a, bq = cur.bq, cq = cur.cq, d = cur.d;
+            const float4 t = cur.t;
+            if (!vx) bq = d = make_float4(0.f, 0.f, 0.f, 0.f);           // ATen skips the out-of-range taps
+            if (!vy) cq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!vy) d = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 gq;
+            auto chan = [&](float v00, float v01, float v10, float v11, float tv, float& gout) {
+                const float val = v00 * tp.nw + v01 * tp.ne + v10 * tp.sw + v11 * tp.se;
+                const float dix = (v01 - v00) * ey + (v11 - v10) * ay;
+                const float diy = (v10 - v00) * ex + (v11 - v01) * ax;
+                const float df = val - tv;
+                const float gvv = up * df * rsqrt_approx(fmaf(df, df, kL1Eps2));       // d loss / d warped value
+                gix = fmaf(gvv, dix, gix);
+                giy = fmaf(gvv, diy, giy);
+                gout = gvv;
+            };
+            chan(a.x, bq.x, cq.x, d.x, t.x, gq.x);
+            chan(a.y, bq.y, cq.y, d.y, t.y, gq.y);
+            chan(a.z, bq.z, cq.z, d.z, t.z, gq.z);
+            chan(a.w, bq.w, cq.w, d.w, t.w, gq.w);
+            if (dtg) st4(dtg + (size_t)pix * C + c, make_float4(-gq.x, -gq.y, -gq.z, -gq.w));
+            if (Gb) st4(Gb + (size_t)pix * C + c, gq);
+        }
+        if (ck == nchunk - 1) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                gix += __shfl_xor_sync(0xffffffffu, gix, o);
+                giy += __shfl_xor_sync(0xffffffffu, giy, o);
+            }
+            if (l16 == 0) s_gxy[wq][pl] = make_float2(gix, giy);
+            gix = giy = 0.f;
+        }
+    };
+    {
+        Rows ra, rb;
+        fetch(half, min(cl, C - 4), ra);
+        for (int it = 0; it < nsteps; it += 2) {
+            step(it, ra, rb);
+            step(it + 1, rb, ra);
+        }
+    }
+    __syncwarp();
+    // ---- lane = pixel: projection / depth adjoint
+    float aP[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) aP[k] = 0.f;
+    if (active) {
+        const float2 gxy = s_gxy[wq][lane];
+        const float gu = gxy.x * pr.mx, gv = gxy.y * pr.my;
+        const float rz = rcp_newton(pr.z);
+        const float gp0 = gu * rz, gp1 = gv * rz, gp2 = -(gu * pr.u + gv * pr.v) * rz;
+        aP[0] = gp0 * g.X0; aP[1] = gp0 * g.X1; aP[2] = gp0 * g.X2; aP[3] = gp0;
+        aP[4] = gp1 * g.X0; aP[5] = gp1 * g.X1; aP[6] = gp1 * g.X2; aP[7] = gp1;
+        aP[8] = gp2 * g.X0; aP[9] = gp2 * g.X1; aP[10] = gp2 * g.X2; aP[11] = gp2;
+        const float gX0 = Pf[0] * gp0 + Pf[4] * gp1 + Pf[8] * gp2;
+        const float gX1 = Pf[1] * gp0 + Pf[5] * gp1 + Pf[9] * gp2;
+        const float gX2 = Pf[2] * gp0 + Pf[6] * gp1 + Pf[10] * gp2;
+        const float gD = gX0 * g.r0 + gX1 * g.r1 + gX2 * g.r2;
+        const float gdisp = -p.range * g.D * g.D * gD;
+        float* dd = p.d_disp + (size_t)b * p.dh * p.dw;
+        if (p.dh == h && p.dw == w) {
+            dd[mypix] = gdisp;                               // identity resize: plain store, no atomics
+        } else {                                             // adjoint of the bilinear resize (d_disp was zeroed)
+            const float hy = 1.f - ut.ly, hx = 1.f - ut.lx;
+            atomicAdd(dd + (size_t)ut.y0 * p.dw + ut.x0, hy * hx * gdisp);
+            atomicAdd(dd + (size_t)ut.y0 * p.dw + ut.x1, hy * ut.lx * gdisp);
+            atomicAdd(dd + (size_t)ut.y1 * p.dw + ut.x0, ut.ly * hx * gdisp);
+            atomicAdd(dd + (size_t)ut.y1 * p.dw + ut.x1, ut.ly * ut.lx * gdisp);
+        }
+    }
+    for (int f = 0; f < S; ++f) {
+        float a2[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) a2[k] = (active && f == fsel) ? aP[k] : 0.f;
+        float tot;
+        const int slot = warp_sum12(a2, tot);
+        if (slot >= 0 && tot != 0.f) atomicAdd(&s_dP[f * 12 + slot], tot);
+    }
+    __syncthreads();
+    float* dPo = kGrad ? p.dP_acc : p.dP;                    // bucketed path: accumulated in the zeroed scratch header
+    if (tid < S * 12 && s_dP[tid] != 0.f) atomicAdd(dPo + (size_t)b * S * 12 + tid, s_dP[tid]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// d_src as a GATHER over the registered taps: a warp owns 32 consecutive source pixels of one (frame, image); per
+// pixel a half-warp adds weight * row of g (the row of -d_tgt when d_tgt was requested: the sign is folded into the
+// weight) for up to kFeatBucketCap taps -- all eight row loads are issued before the first use -- and writes the C-row of
+// d_src.  No memset of d_src, no float atomics, no transposition (the NCHW kernel needs a shared-memory tile for that).
+template <typename T>
+__global__ void __launch_bounds__(f2::NT) feat_gather_nhwc_kernel(const FeatDev p) {
+    using namespace f2;
+    __shared__ int2 s_ent[NT / 32][PIX][kFeatBucketCap];
+    __shared__ int s_n[NT / 32][PIX];
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5, half = lane >> 4, l16 = lane & 15;
+    const int fb = blockIdx.y;                               // frame * B + b
+    const int f = fb / p.B, b = fb - f * p.B;
+    const int hw = p.h * p.w, C = p.C;
+    if (blockIdx.x == 0 && blockIdx.y == 0)                  // dP of the per-pixel kernel: scratch accumulator -> output
+        for (int i = tid; i < p.B * p.S * 12; i += NT) p.dP[i] = p.dP_acc[i];
+    const int o0 = (blockIdx.x * (NT / 32) + wq) * PIX;
+    if (o0 >= hw) return;
+    {
+        const int o = min(o0 + lane, hw - 1);
+        const int n = (o0 + lane < hw) ? min(__ldg(p.bk_cnt + (size_t)fb * hw + o), kFeatBucketCap) : 0;
+        const int4* e4 = reinterpret_cast<const int4*>(p.bk_ent + ((size_t)fb * hw + o) * kFeatBucketCap);
+        s_n[wq][lane] = n;
+#pragma unroll
+        for (int k = 0; k < kFeatBucketCap / 2; ++k) {
+            const int4 e = __ldg(e4 + k);
+            s_ent[wq][lane][2 * k] = make_int2(e.x, e.y);
+            s_ent[wq][lane][2 * k + 1] = make_int2(e.z, e.w);
+        }
+    }
+    __syncwarp();
+    const bool from_dtgt = p.d_tgt != nullptr;               // g = -d_tgt
+    const T* Gb = reinterpret_cast<const T*>(from_dtgt ? p.d_tgt : p.G) + (size_t)b * hw * C;
+    const float sgn = from_dtgt ? -1.f : 1.f;
+    float* dsf = p.d_src[0];
+#pragma unroll
+    for (int k = 1; k < TDL_MAX_SRC; ++k)
+        if (k == f) dsf = p.d_src[k];
+    T* dst = reinterpret_cast<T*>(dsf) + (size_t)b * hw * C;
+    for (int q = 0; q < PIX; q += 2) {
+        const int pl = q + half;
+        const int o = o0 + pl;
+        if (o >= hw) continue;
+        const int n = s_n[wq][pl];
+        for (int c = 4 * l16; c < C; c += 64) {
+            // the rows of the registered taps only (n is the same for the 16 lanes of a pixel), all requested before the first use
+            float4 rows[kFeatBucketCap];
+            float wgt[kFeatBucketCap];
+#pragma unroll
+            for (int k = 0; k < kFeatBucketCap; ++k) {
+                if (k < n) {
+                    const int2 e = s_ent[wq][pl][k];
+                    wgt[k] = sgn * __int_as_float(e.y);
+                    rows[k] = ld4(Gb + (size_t)e.x * C + c);
+                }
+            }
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < kFeatBucketCap; ++k) {
+                if (k < n) {
+                    acc.x = fmaf(wgt[k], rows[k].x, acc.x);
+                    acc.y = fmaf(wgt[k], rows[k].y, acc.y);
+                    acc.z = fmaf(wgt[k], rows[k].z, acc.z);
+                    acc.w = fmaf(wgt[k], rows[k].w, acc.w);
+                }
+            }
+            st4(dst + (size_t)o * C + c, acc);
+        }
+    }
+}
+
+// taps beyond a bucket's slots (border pixels that collect every clipped sample): read-modify-write by ONE thread
+// group per list entry; entries of one source pixel are rare enough that plain atomics on fp32 / CAS on bf16 pairs do
+template <typename T>
+__global__ void __launch_bounds__(256) feat_overflow_nhwc_kernel(const FeatDev p) {
+    const int b = blockIdx.y;
+    const int n = p.ov_cnt[b];
+    const int ngrp = (int)(gridDim.x * blockDim.x) >> 4;
+    const int l16 = threadIdx.x & 15;
+    const int hw = p.h * p.w, C = p.C;
+    const int4* list = p.ov_ent + (size_t)b * 4 * hw;
+    const bool from_dtgt = p.d_tgt != nullptr;
+    const T* Gb = reinterpret_cast<const T*>(from_dtgt ? p.d_tgt : p.G) + (size_t)b * hw * C;
+    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) >> 4; i < n; i += ngrp) {
+        const int4 e = list[i];                              // (frame, source pixel, target pixel, weight)
+        float* dsf = p.d_src[0];
+#pragma unroll
+        for (int k = 1; k < TDL_MAX_SRC; ++k)
+            if (k == e.x) dsf = p.d_src[k];
+        T* dst = reinterpret_cast<T*>(dsf) + ((size_t)b * hw + e.y) * C;
+        const float wgt = (from_dtgt ? -1.f : 1.f) * __int_as_float(e.w);
+        for (int c = 4 * l16; c < C; c += 64) {
+            const float4 gv = f2::ld4(Gb + (size_t)e.z * C + c);
+            if (sizeof(T) == 4) {
+                float* d4 = reinterpret_cast<float*>(dst) + c;
+                atomicAdd(d4 + 0, wgt * gv.x);
+                atomicAdd(d4 + 1, wgt * gv.y);
+                atomicAdd(d4 + 2, wgt * gv.z);
+                atomicAdd(d4 + 3, wgt * gv.w);
+            } else {
+                __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(dst) + c);
+                atomicAdd(d2 + 0, __floats2bfloat162_rn(wgt * gv.x, wgt * gv.y));
+                atomicAdd(d2 + 1, __floats2bfloat162_rn(wgt * gv.z, wgt * gv.w));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t fwd_t(const FeatDev& p, cudaStream_t st) {
+    using namespace f2;
+    dim3 grid((unsigned)((p.h * p.w + NT - 1) / NT), p.B);
+    switch (p.S) {
+        case 1: feat_fwd_nhwc_kernel<1, T><<<grid, NT, 0, st>>>(p); break;
+        case 2: feat_fwd_nhwc_kernel<2, T><<<grid, NT, 0, st>>>(p); break;
+        case 3: feat_fwd_nhwc_kernel<3, T><<<grid, NT, 0, st>>>(p); break;
+        case 4: feat_fwd_nhwc_kernel<4, T><<<grid, NT, 0, st>>>(p); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_feat_fwd_nhwc(const FeatDev& p, cudaStream_t st) {
+    return p.dtype == TDL_DTYPE_BF16 ? fwd_t<__nv_bfloat16>(p, st) : fwd_t<float>(p, st);
+}
+
+cudaError_t launch_feat_bwd_nhwc(const FeatDev& p, cudaStream_t st) {
+    using namespace f2;
+    dim3 grid((unsigned)((p.h * p.w + NT - 1) / NT), p.B);
+    const bool grad = p.bk_cnt != nullptr;                   // d_src requested: register taps for the gather
+    if (p.dtype == TDL_DTYPE_BF16) {
+        if (grad) feat_bwd_nhwc_kernel<true, __nv_bfloat16><<<grid, NT, 0, st>>>(p);
+        else feat_bwd_nhwc_kernel<false, __nv_bfloat16><<<grid, NT, 0, st>>>(p);
+    } else {
+        if (grad) feat_bwd_nhwc_kernel<true, float><<<grid, NT, 0, st>>>(p);
+        else feat_bwd_nhwc_kernel<false, float><<<grid, NT, 0, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_feat_gather_nhwc(const FeatDev& p, cudaStream_t st) {
+    using namespace f2;
+    dim3 grid((unsigned)((p.h * p.w + NT - 1) / NT), p.S * p.B);
+    if (p.dtype == TDL_DTYPE_BF16) feat_gather_nhwc_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(p);
+    else feat_gather_nhwc_kernel<float><<<grid, NT, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_feat_overflow_nhwc(const FeatDev& p, cudaStream_t st) {
+    dim3 grid((148 * 8 + p.B - 1) / p.B, p.B);
+    if (p.dtype == TDL_DTYPE_BF16) feat_overflow_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
+    else feat_overflow_nhwc_kernel<float><<<grid, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace tdl

@@ -91,6 +91,7 @@ struct SmoothDev {
 // ---- feature-metric ----------------------------------------------------------------
 struct FeatDev {
     int B, C, h, w, S;
+    int layout, dtype;           // TDL_LAYOUT_* / TDL_DTYPE_* of tgt, src, warped, d_tgt, d_src (bf16 pointers are carried as float*)
     int Bnorm;                   // batch size of the mean (== B except for the batch chunks of the bucketed backward)
     int dh, dw;
     float sy, sx;
@@ -154,6 +155,11 @@ cudaError_t launch_feat_finalize(const FeatDev& p, cudaStream_t st);
 cudaError_t launch_feat_bwd(const FeatDev& p, cudaStream_t st);
 cudaError_t launch_feat_bwd_gather(const FeatDev& p, cudaStream_t st);      // after launch_feat_bwd when p.G != nullptr
 cudaError_t launch_feat_bwd_overflow(const FeatDev& p, cudaStream_t st);    // after the gather
+// channel-last (NHWC) feature maps, fp32 or bf16 storage (tdl_feat2.cu)
+cudaError_t launch_feat_fwd_nhwc(const FeatDev& p, cudaStream_t st);
+cudaError_t launch_feat_bwd_nhwc(const FeatDev& p, cudaStream_t st);
+cudaError_t launch_feat_gather_nhwc(const FeatDev& p, cudaStream_t st);
+cudaError_t launch_feat_overflow_nhwc(const FeatDev& p, cudaStream_t st);
 cudaError_t launch_edge_finalize(const double* acc, int acc_stride, int B, float first_coef, float second_coef,
                                  int h, int w, float* loss, cudaStream_t st);
 

@@ -178,6 +178,34 @@ class FeatConfig:
     align_corners: bool = False
     coef: float = 1e-3                  # perception_weight (/ len(scales) in mono_fm)
     materialize: bool = True            # write outputs[("feature",f,0)] and the argmin map
+    layout: str = "auto"                # "auto": channel-last kernels when the target features ARE channels_last (what a
+                                        # channels_last extractor hands over) or bf16; "nchw" / "nhwc" force one (with a copy)
+
+
+def _feat_plan(cfg, tgt):
+    """-> (nhwc: bool, torch dtype) of the feature tensors handed to tdl_feat_*."""
+    C = tgt.shape[1]
+    bf16 = tgt.dtype == torch.bfloat16
+    is_cl = tgt.dim() == 4 and tgt.is_contiguous(memory_format=torch.channels_last) and not tgt.is_contiguous()
+    if cfg.layout == "nhwc" or bf16:
+        nhwc = True
+    elif cfg.layout == "nchw":
+        nhwc = False
+    else:
+        nhwc = is_cl
+    if nhwc and C % 4 != 0:
+        if bf16:
+            raise _lib.TdlError("bf16 feature maps need C % 4 == 0")
+        nhwc = False
+    return nhwc, (torch.bfloat16 if bf16 else torch.float32)
+
+
+def _feat_tensor(t, name, nhwc, dtype):
+    if not t.is_cuda:
+        raise _lib.TdlError(f"{name}: expected a CUDA tensor (the fused loss has no CPU implementation)")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous(memory_format=torch.channels_last) if nhwc else t.contiguous()
 
 
 class FeatureMetricLoss(torch.autograd.Function):
@@ -187,11 +215,12 @@ class FeatureMetricLoss(torch.autograd.Function):
     def forward(ctx, cfg: FeatConfig, tgt, disp, P, invK, *srcs):
         L = _lib.lib()
         S = cfg.n_src
-        tgt = _f32c(tgt, "tgt_feat")
+        nhwc, fdtype = _feat_plan(cfg, tgt)
+        tgt = _feat_tensor(tgt, "tgt_feat", nhwc, fdtype)
         disp = _f32c(disp, "disp")
         P = _f32c(P, "P")
         invK = _f32c(invK, "invK")
-        srcs = [_f32c(t, "src_feat") for t in srcs]
+        srcs = [_feat_tensor(t, "src_feat", nhwc, fdtype) for t in srcs]
         if len(srcs) != S or not 1 <= S <= TDL_MAX_SRC:
             raise _lib.TdlError("src_feat: wrong number of source frames")
         B, Cc, h, w = tgt.shape
@@ -201,6 +230,8 @@ class FeatureMetricLoss(torch.autograd.Function):
         a.B, a.C, a.h, a.w, a.S = B, Cc, h, w, S
         a.disp_h, a.disp_w = disp.shape[2], disp.shape[3]
         a.align_corners = int(cfg.align_corners)
+        a.layout = _lib.TDL_LAYOUT_NHWC if nhwc else _lib.TDL_LAYOUT_NCHW
+        a.dtype = _lib.TDL_DTYPE_BF16 if fdtype == torch.bfloat16 else _lib.TDL_DTYPE_F32
         a.min_depth, a.max_depth, a.coef = cfg.min_depth, cfg.max_depth, cfg.coef
         a.tgt, a.disp, a.P, a.invK = tgt.data_ptr(), disp.data_ptr(), P.data_ptr(), invK.data_ptr()
         warped, extra = [], []
@@ -223,6 +254,7 @@ class FeatureMetricLoss(torch.autograd.Function):
         with torch.cuda.device(tgt.device):
             _lib.check(L.tdl_feat_fwd(C.byref(a), _stream()), "tdl_feat_fwd")
         ctx.cfg = cfg
+        ctx.nhwc = nhwc
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(tgt, disp, P, invK, ws, *srcs)
         ctx.mark_non_differentiable(*warped, *extra)
@@ -243,6 +275,8 @@ class FeatureMetricLoss(torch.autograd.Function):
         a.B, a.C, a.h, a.w, a.S = B, Cc, h, w, S
         a.disp_h, a.disp_w = disp.shape[2], disp.shape[3]
         a.align_corners = int(cfg.align_corners)
+        a.layout = _lib.TDL_LAYOUT_NHWC if ctx.nhwc else _lib.TDL_LAYOUT_NCHW
+        a.dtype = _lib.TDL_DTYPE_BF16 if tgt.dtype == torch.bfloat16 else _lib.TDL_DTYPE_F32
         a.min_depth, a.max_depth, a.coef = cfg.min_depth, cfg.max_depth, cfg.coef
         a.tgt, a.disp, a.P, a.invK = tgt.data_ptr(), disp.data_ptr(), P.data_ptr(), invK.data_ptr()
         for f, t in enumerate(srcs):
