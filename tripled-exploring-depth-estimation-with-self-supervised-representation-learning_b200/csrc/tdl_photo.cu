@@ -20,6 +20,7 @@
 // mono/model/mono_fm/layers.py:57-107 (see include/tdl.h).
 #include "tdl_common.cuh"
 #include "tdl_internal.h"
+#include "tdl_ssim.cuh"
 #include "tdl_tma.cuh"
 
 namespace tdl {
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_fwd_kernel(const PhotoDev p) {
     const int b = blockIdx.z, tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
     const int H = p.H, W = p.W;
     const size_t HW = (size_t)H * W;
+    const ProjConst pcst = make_proj_const(H, W, p.align_corners);      // (IEEE divisions: once per kernel, not per loop)
 
     if (tid < S * 12) s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
     if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_fwd_kernel(const PhotoDev p) {
                 const Geo g = backproject(up_value(db, w, ut), dp, s_iK, px, py);
 #pragma unroll
                 for (int f = 0; f < S; ++f) {
-                    const Proj pr = project<false>(g, s_cam + f * 12, H, W, p.align_corners);
+                    const Proj pr = project<false>(g, s_cam + f * 12, pcst);
                     const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
                     const float* sb = p.src[f] + (size_t)b * 3 * HW;
 #pragma unroll
@@ -350,6 +352,7 @@ __global__ void __launch_bounds__(256, 1) photo_warp_kernel(const PhotoDev p) {
     const int b = blockIdx.y;
     const int H = p.H, W = p.W;
     const size_t HW = (size_t)H * W;
+    const ProjConst pcst = make_proj_const(H, W, p.align_corners);      // (IEEE divisions: once per kernel, not per loop)
     if (tid < S * 12) s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
     if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
     __syncthreads();
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(256, 1) photo_warp_kernel(const PhotoDev p) {
             float v[S][3][4];
 #pragma unroll
             for (int f = 0; f < S; ++f) {
-                const Proj pr = project<false>(g, s_cam + f * 12, H, W, p.align_corners);
+                const Proj pr = project<false>(g, s_cam + f * 12, pcst);
                 bt[f] = bilin_taps(pr.ix, pr.iy, H, W);
                 // block-uniform 64-bit base + 32-bit per-thread offsets: one integer add per access
                 const float* sb = p.src[f] + (size_t)b * 3 * HW;
@@ -647,9 +650,16 @@ __global__ void __launch_bounds__(kNT, 2) photo_score_kernel(const PhotoDev p, c
 }
 
 
-// SSIM window adjoint: for the 3x3 window centred at xs / ys (pitch PITCH) returns k * (dS/dmu_x, dS/dE[x^2],
-// dS/dE[xy]) (G_mu, G_a, G_c), zero where torch.clamp blocks the gradient.  The window
-// statistics use the forward's row-major order so that the clamp decision is the forward's.
+// SSIM window adjoint: for the 3x3 window centred at xs / ys (pitch PITCH) returns the coefficients (cA, cB, cC) with
+//     d (k_in * 9 * v) / d x_q = cA + 2 x_q cB + y_q cC          for every pixel q of the window,
+// v = clamp((1 - SSIM)/2, 0, 1) (G_mu, G_a, G_c), zero where torch.clamp blocks the gradient.
+// Round 2: the five window sums are accumulated with fused multiply-adds and SSIM is evaluated on the raw 9-sums
+// (tdl_ssim.cuh: numerator and denominator scaled by 81^2, no divisions by 9, K1 / K2 only ever added to exact
+// products): ~100 instructions per window and channel instead of ~145 for the ATen-ordered sums of round 1, which were
+// 36 % of this kernel's 292 M warp-instructions on the scene workload (profiles/r2_*).  The callers pass k = g / 9 (the
+// factor of the mean over the window, kept from round 1): with the scaled sums Sx = 9 mu_x ... the chain rule gives
+//     d v / d x_q = [ q Sx (d2 - d1) - Sy (n2 - n1) ] / d  +  x_q * 9 q d1 / d  +  y_q * (-9 n1 / d),      q = n / d,
+// so cA = 9k (...)/d, 2 cB = 9k * 9 q d1 / d, cC = -9k * 9 n1 / d.
 template <int PITCH>
 TDL_DEV void window_adjoint(const float* __restrict__ xs, const float* __restrict__ ys, float k, float& cA, float& cB,
                             float& cC) {
@@ -659,30 +669,27 @@ TDL_DEV void window_adjoint(const float* __restrict__ xs, const float* __restric
 #pragma unroll
         for (int dx = -1; dx <= 1; ++dx) {
             const float xv = xs[dy * PITCH + dx], yv = ys[dy * PITCH + dx];
-            const bool first = dy == -1 && dx == -1;
-            sx = first ? xv : __fadd_rn(sx, xv);
-            sy = first ? yv : __fadd_rn(sy, yv);
-            sxx = first ? __fmul_rn(xv, xv) : __fadd_rn(sxx, __fmul_rn(xv, xv));
-            syy = first ? __fmul_rn(yv, yv) : __fadd_rn(syy, __fmul_rn(yv, yv));
-            sxy = first ? __fmul_rn(xv, yv) : __fadd_rn(sxy, __fmul_rn(xv, yv));
+            sx += xv;
+            sy += yv;
+            sxx = fmaf(xv, xv, sxx);
+            syy = fmaf(yv, yv, syy);
+            sxy = fmaf(xv, yv, sxy);
         }
     }
-    const float mu_x = div9(sx), mu_y = div9(sy);
-    const float sg_x = __fsub_rn(div9(sxx), __fmul_rn(mu_x, mu_x));
-    const float sg_y = __fsub_rn(div9(syy), __fmul_rn(mu_y, mu_y));
-    const float sg_xy = __fsub_rn(div9(sxy), __fmul_rn(mu_x, mu_y));
-    const float n1 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, mu_x), mu_y), kSsimC1);
-    const float n2 = __fadd_rn(__fmul_rn(2.f, sg_xy), kSsimC2);
-    const float d1 = __fadd_rn(__fadd_rn(__fmul_rn(mu_x, mu_x), __fmul_rn(mu_y, mu_y)), kSsimC1);
-    const float d2 = __fadd_rn(__fadd_rn(sg_x, sg_y), kSsimC2);
+    const float n1 = fmaf(sx, sy, fmaf(sx, sy, kK1));
+    const float d1 = fmaf(sx, sx, fmaf(sy, sy, kK1));
+    const float n2 = fmaf(-sx, sy, fmaf(9.f, sxy, fmaf(9.f, sxy, fmaf(-sx, sy, kK2))));
+    const float d2 = fmaf(-sx, sx, fmaf(9.f, sxx, fmaf(9.f, syy, fmaf(-sy, sy, kK2))));
     const float n = __fmul_rn(n1, n2), d = __fmul_rn(d1, d2);
-    const float v = __fmul_rn(__fsub_rn(1.f, div_rn(n, d)), 0.5f);        // identical to the forward
+    const float e = __fsub_rn(d, n);                           // v = e / (2 d): the clamp passes gradient for 0 <= v <= 1
     cA = cB = cC = 0.f;
-    if (v >= 0.f && v <= 1.f) {                                            // clamp passes gradient inside [0,1]
-        const float rd = __frcp_rn(d);
-        cA = k * ((-mu_y * (n2 - n1) + (n * rd) * mu_x * (d2 - d1)) * rd);
-        cB = k * (n * d1 * 0.5f * rd * rd);
-        cC = k * (-n1 * rd);
+    if (e >= 0.f && e <= 2.f * d) {
+        const float rd = rcp_newton(d);
+        const float q = n * rd;
+        const float k9 = 9.f * k * rd;
+        cA = k9 * fmaf(q * sx, d2 - d1, -sy * (n2 - n1));
+        cB = 4.5f * k9 * q * d1;
+        cC = -9.f * k9 * n1;
     }
 }
 
@@ -718,6 +725,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
     const int H = p.H, W = p.W;
     const size_t HW = (size_t)H * W;
+    const ProjConst pcst = make_proj_const(H, W, p.align_corners);      // (IEEE divisions: once per kernel, not per loop)
     const int h = p.dh[s], w = p.dw[s];
     const float up = __ldg(p.dlosses + s) * p.photo_coef[s] / ((float)p.B * (float)H * (float)W);
 
@@ -849,7 +857,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
                 const Geo g = backproject(up_value(db, w, ut), dp, s_iK, px, py);
 #pragma unroll
                 for (int f = 0; f < S; ++f) {
-                    const Proj pr = project<false>(g, s_cam + f * 12, H, W, p.align_corners);
+                    const Proj pr = project<false>(g, s_cam + f * 12, pcst);
                     const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
                     const float* sb = p.src[f] + (size_t)b * 3 * HW;
 #pragma unroll
@@ -944,7 +952,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
             sbase += (size_t)b * 3 * HW;
             const UpTap ut = up_tap(py, px, p.sy[s], p.sx[s], h, w);
             const Geo g = backproject(up_value(db, w, ut), dp, s_iK, px, py);
-            const Proj pr = project<true>(g, Pf, H, W, p.align_corners);
+            const Proj pr = project<true>(g, Pf, pcst);
             const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
             const float* q = sbase + (size_t)bt.y0 * W + bt.x0;
             const int dx = bt.vx ? 1 : 0, dy = bt.vy ? W : 0;
@@ -961,7 +969,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
                 giy += Gc * diy;
             }
             const float gu = gix * pr.mx, gv = giy * pr.my;
-            const float rz = __frcp_rn(pr.z);
+            const float rz = rcp_newton(pr.z);
             const float gp0 = gu * rz, gp1 = gv * rz, gp2 = -(gu * pr.u + gv * pr.v) * rz;
             float aP[12];
             aP[0] = gp0 * g.X0; aP[1] = gp0 * g.X1; aP[2] = gp0 * g.X2; aP[3] = gp0;
@@ -1094,7 +1102,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
             for (int u = 0; u < 2; ++u) {
                 const int i = i0 + u, gy = ty0 + r0 + i;
                 act[u] = gx < W && gy < H && (G[0][i] != 0.f || G[1][i] != 0.f || G[2][i] != 0.f);
-                pr[u] = project<true>(geo[i], Pf, H, W, p.align_corners);
+                pr[u] = project<true>(geo[i], Pf, pcst);
                 bt[u] = bilin_taps(pr[u].ix, pr[u].iy, H, W);
             }
 #pragma unroll
@@ -1127,7 +1135,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
                         giy += G[ch][i] * diy;
                     }
                     const float gu = gix * pr[u].mx, gv = giy * pr[u].my;
-                    const float rz = __frcp_rn(pr[u].z);
+                    const float rz = rcp_newton(pr[u].z);
                     const float gp0 = gu * rz, gp1 = gv * rz, gp2 = -(gu * pr[u].u + gv * pr[u].v) * rz;
                     aP[0] += gp0 * g.X0; aP[1] += gp0 * g.X1; aP[2] += gp0 * g.X2; aP[3] += gp0;
                     aP[4] += gp1 * g.X0; aP[5] += gp1 * g.X1; aP[6] += gp1 * g.X2; aP[7] += gp1;
