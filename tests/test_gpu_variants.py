@@ -84,6 +84,13 @@ def test_generate_images_pred_standalone():
     for f in (-1, 1):
         assert ("color", f, 2) in outputs and ("color", f, 0) not in outputs
         assert rel_l2(outputs[("color", f, 2)].cpu(), ref_out[("color", f, 2)].detach()) < 1e-5
+    # the warped images carry no autograd history: asking for them with inputs that require grad is an error, not a
+    # silent no-op (a subclass building its own term on outputs[("color", f, s)] would otherwise train nothing) ...
+    outputs[("disp", 0, 2)] = outputs[("disp", 0, 2)].detach().requires_grad_(True)
+    with pytest.raises(RuntimeError, match="without autograd history"):
+        net.generate_images_pred(inputs, outputs, 2)
+    with torch.no_grad():                      # ... and fine when the caller says it only inspects them
+        net.generate_images_pred(inputs, outputs, 2)
 
 
 def test_reference_noise_mode_reproduces_reference_rng_stream():

@@ -64,6 +64,13 @@ class EdgeArgs(C.Structure):
     ]
 
 
+TDL_MAX_LEVELS = 5
+
+
+class EdgeMultiArgs(C.Structure):
+    _fields_ = [("nlevels", C.c_int32), ("reserved0", C.c_int32), ("level", EdgeArgs * TDL_MAX_LEVELS)]
+
+
 class ReconArgs(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("coef", C.c_float),
@@ -88,7 +95,7 @@ class KernelTime(C.Structure):
 EXPORTS = ["tdl_abi_version", "tdl_strerror", "tdl_set_option", "tdl_get_option", "tdl_launch_count", "tdl_profile_begin", "tdl_profile_end",
            "tdl_photo_ws_bytes", "tdl_photo_fwd", "tdl_photo_bwd",
            "tdl_feat_ws_bytes", "tdl_feat_bwd_scratch_bytes", "tdl_feat_fwd", "tdl_feat_bwd",
-           "tdl_edge_ws_bytes", "tdl_edge_smooth_fwd", "tdl_edge_smooth_bwd",
+           "tdl_edge_ws_bytes", "tdl_edge_smooth_fwd", "tdl_edge_smooth_bwd", "tdl_edge_smooth_multi_fwd", "tdl_edge_smooth_multi_bwd",
            "tdl_recon_ws_bytes", "tdl_recon_fwd", "tdl_recon_bwd", "tdl_pose_fwd", "tdl_pose_bwd"]
 
 _lib = None
@@ -132,6 +139,7 @@ def lib():
     for name, T in (("tdl_photo_fwd", PhotoArgs), ("tdl_photo_bwd", PhotoArgs),
                     ("tdl_feat_fwd", FeatArgs), ("tdl_feat_bwd", FeatArgs),
                     ("tdl_edge_smooth_fwd", EdgeArgs), ("tdl_edge_smooth_bwd", EdgeArgs),
+                    ("tdl_edge_smooth_multi_fwd", EdgeMultiArgs), ("tdl_edge_smooth_multi_bwd", EdgeMultiArgs),
                     ("tdl_recon_fwd", ReconArgs), ("tdl_recon_bwd", ReconArgs),
                     ("tdl_pose_fwd", PoseArgs), ("tdl_pose_bwd", PoseArgs)):
         fn = getattr(L, name)

@@ -273,6 +273,8 @@ int tdl_launch_count(const char* entry) {
     if (!strcmp(entry, "tdl_feat_bwd:gather")) return 3;  // feat_bwd (bucket) + feat_gather + feat_overflow (bwd_scratch given)
     if (!strcmp(entry, "tdl_edge_smooth_fwd")) return 3;  // area pyramid, smooth_fwd, finalize
     if (!strcmp(entry, "tdl_edge_smooth_bwd")) return 1;
+    if (!strcmp(entry, "tdl_edge_smooth_multi_fwd")) return 3;   // all levels: area pyramids, smooth_fwd, finalize
+    if (!strcmp(entry, "tdl_edge_smooth_multi_bwd")) return 1;
     if (!strcmp(entry, "tdl_recon_fwd")) return 2;        // recon_fwd, finalize
     if (!strcmp(entry, "tdl_recon_bwd")) return 1;
     if (!strcmp(entry, "tdl_pose_fwd") || !strcmp(entry, "tdl_pose_bwd")) return 1;
@@ -570,6 +572,48 @@ int tdl_edge_smooth_bwd(const tdl_edge_args* a, tdl_stream_t stream) {
     SmoothDev sm;
     float* J;
     int rc = check_edge(a, true, &sm, &J);
+    if (rc == TDL_OK) rc = check_device();
+    if (rc != TDL_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDL_KERNEL("edge_smooth_bwd", launch_smooth_bwd(sm, st));
+    return TDL_OK;
+}
+
+static int check_edge_multi(const tdl_edge_multi_args* m, bool bwd, SmoothDev* sm) {
+    if (!m) return TDL_ERR_NULL;
+    if (m->nlevels < 1 || m->nlevels > TDL_MAX_LEVELS) return TDL_ERR_COUNT;
+    memset(sm, 0, sizeof(*sm));
+    for (int l = 0; l < m->nlevels; ++l) {
+        SmoothDev one;
+        float* J;
+        const int rc = check_edge(&m->level[l], bwd, &one, &J);
+        if (rc != TDL_OK) return rc;
+        const tdl_edge_args& a = m->level[l];
+        if (a.B != m->level[0].B || a.H != m->level[0].H || a.W != m->level[0].W || a.image != m->level[0].image) return TDL_ERR_SHAPE;
+        sm->lv[l] = one.lv[0];
+    }
+    sm->B = m->level[0].B;
+    sm->nlevels = m->nlevels;
+    return TDL_OK;
+}
+
+int tdl_edge_smooth_multi_fwd(const tdl_edge_multi_args* m, tdl_stream_t stream) {
+    SmoothDev sm;
+    int rc = check_edge_multi(m, false, &sm);
+    if (rc == TDL_OK) rc = check_device();
+    if (rc != TDL_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* loss[TDL_MAX_LEVELS];
+    for (int l = 0; l < m->nlevels; ++l) loss[l] = m->level[l].loss;
+    TDL_KERNEL("area_pyramid", launch_area_pyramid_multi(m->level[0].image, m->level[0].H, m->level[0].W, sm, st));
+    TDL_KERNEL("edge_smooth_fwd", launch_smooth_fwd(sm, st));
+    TDL_KERNEL("edge_finalize", launch_edge_finalize_multi(sm, loss, st));
+    return TDL_OK;
+}
+
+int tdl_edge_smooth_multi_bwd(const tdl_edge_multi_args* m, tdl_stream_t stream) {
+    SmoothDev sm;
+    int rc = check_edge_multi(m, true, &sm);
     if (rc == TDL_OK) rc = check_device();
     if (rc != TDL_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

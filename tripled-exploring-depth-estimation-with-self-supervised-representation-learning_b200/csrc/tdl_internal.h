@@ -85,7 +85,7 @@ struct SmoothDev {
     int B, nlevels;
     float* zero_ptr;       // optional: zero_n floats cleared by the first CTA (folds a tiny memset of the NEXT kernel's
     int zero_n;            // accumulator into this launch; stream order makes it visible)
-    SmoothLevel lv[TDL_MAX_SCALES];
+    SmoothLevel lv[TDL_MAX_LEVELS];      // disparity scales (<= TDL_MAX_SCALES) or encoder levels
 };
 
 // ---- feature-metric ----------------------------------------------------------------
@@ -148,6 +148,9 @@ cudaError_t launch_photo_bwd(const PhotoDev& p, cudaStream_t st);
 cudaError_t launch_smooth_fwd(const SmoothDev& p, cudaStream_t st);
 cudaError_t launch_smooth_bwd(const SmoothDev& p, cudaStream_t st);
 cudaError_t launch_area_pyramid(const float* img, int B, int H, int W, float* J, int h, int w, cudaStream_t st);
+// every level's area-downsampled image in one launch; also zeroes every level's accumulators (lv[l].acc, 4 doubles per image)
+cudaError_t launch_area_pyramid_multi(const float* img, int H, int W, const SmoothDev& p, cudaStream_t st);
+cudaError_t launch_edge_finalize_multi(const SmoothDev& p, float* const* loss, cudaStream_t st);
 cudaError_t launch_photo_finalize(const PhotoDev& p, const float* photo_coef, const float* smooth_coef,
                                   float* losses, cudaStream_t st);
 cudaError_t launch_feat_fwd(const FeatDev& p, cudaStream_t st);

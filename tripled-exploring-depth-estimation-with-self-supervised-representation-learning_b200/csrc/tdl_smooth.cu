@@ -216,6 +216,32 @@ __global__ void __launch_bounds__(256) area_pyramid_kernel(const float* __restri
     J[idx] = acc * (1.f / (float)(fac * fac));
 }
 
+// all levels in one launch (blockIdx.y = level); the first CTA of a level also clears that level's accumulators
+struct PyrLevels {
+    int n, B, H, W;
+    float* J[TDL_MAX_LEVELS];
+    double* acc[TDL_MAX_LEVELS];
+    int h[TDL_MAX_LEVELS], w[TDL_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(256) area_pyramid_multi_kernel(const float* __restrict__ img, const PyrLevels p) {
+    const int l = blockIdx.y;
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < p.B * 4; i += 256) p.acc[l][i] = 0.0;
+    const int h = p.h[l], w = p.w[l], fac = p.H / h;
+    const size_t total = (size_t)p.B * 3 * h * w;
+    for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
+        const int i = idx % w;
+        const int j = (idx / w) % h;
+        const size_t bc = idx / ((size_t)w * h);
+        const float* base = img + bc * (size_t)p.H * p.W + (size_t)j * fac * p.W + (size_t)i * fac;
+        float acc = 0.f;
+        for (int dy = 0; dy < fac; ++dy)
+            for (int dx = 0; dx < fac; ++dx) acc += __ldg(base + (size_t)dy * p.W + dx);
+        p.J[l][idx] = acc * (1.f / (float)(fac * fac));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // final scalars
 __device__ void photo_finalize_body(const double* __restrict__ acc, int B, int nscales, double inv_bhw,
@@ -264,6 +290,27 @@ __global__ void edge_finalize_kernel(const double* __restrict__ acc, int stride,
     }
 }
 
+struct FinLevels {
+    int n, B;
+    const double* acc[TDL_MAX_LEVELS];
+    float c1[TDL_MAX_LEVELS], c2[TDL_MAX_LEVELS];
+    int h[TDL_MAX_LEVELS], w[TDL_MAX_LEVELS];
+    float* loss[TDL_MAX_LEVELS];
+};
+
+__global__ void edge_finalize_multi_kernel(const FinLevels p) {
+    const int l = threadIdx.x;
+    if (l < p.n) {
+        double f1 = 0.0, f2 = 0.0;
+        for (int b = 0; b < p.B; ++b) {
+            f1 += p.acc[l][(size_t)b * 4 + 2];
+            f2 += p.acc[l][(size_t)b * 4 + 3];
+        }
+        p.loss[l][0] = __fadd_rn(__fmul_rn(p.c1[l], nan_if_empty((float)f1, p.h[l] < 2 || p.w[l] < 2)),
+                                 __fmul_rn(p.c2[l], nan_if_empty((float)f2, p.h[l] < 3 || p.w[l] < 3)));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 static void smooth_grid(const SmoothDev& p, dim3& grid) {
     int maxpix = 1;
@@ -288,6 +335,36 @@ cudaError_t launch_smooth_bwd(const SmoothDev& p, cudaStream_t st) {
 cudaError_t launch_area_pyramid(const float* img, int B, int H, int W, float* J, int h, int w, cudaStream_t st) {
     const size_t total = (size_t)B * 3 * h * w;
     area_pyramid_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(img, H, W, J, h, w, H / h, total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_area_pyramid_multi(const float* img, int H, int W, const SmoothDev& p, cudaStream_t st) {
+    PyrLevels a;
+    a.n = p.nlevels; a.B = p.B; a.H = H; a.W = W;
+    size_t most = 1;
+    for (int l = 0; l < p.nlevels; ++l) {
+        a.J[l] = const_cast<float*>(p.lv[l].J);
+        a.acc[l] = p.lv[l].acc;
+        a.h[l] = p.lv[l].h;
+        a.w[l] = p.lv[l].w;
+        most = max(most, (size_t)p.B * 3 * p.lv[l].h * p.lv[l].w);
+    }
+    area_pyramid_multi_kernel<<<dim3((unsigned)((most + 255) / 256), p.nlevels), 256, 0, st>>>(img, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_edge_finalize_multi(const SmoothDev& p, float* const* loss, cudaStream_t st) {
+    FinLevels a;
+    a.n = p.nlevels; a.B = p.B;
+    for (int l = 0; l < p.nlevels; ++l) {
+        a.acc[l] = p.lv[l].acc;
+        a.c1[l] = p.lv[l].first_coef;
+        a.c2[l] = p.lv[l].second_coef;
+        a.h[l] = p.lv[l].h;
+        a.w[l] = p.lv[l].w;
+        a.loss[l] = loss[l];
+    }
+    edge_finalize_multi_kernel<<<1, 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -31,7 +31,7 @@ import torch
 from .geometry import half_res_intrinsics, projection_matrix
 import torch.nn.functional as F
 
-from .ops import (EdgeAwareSmoothness, EdgeConfig, FeatConfig, FeatureMetricLoss, MaskedReconstructionLoss,
+from .ops import (EdgeAwareSmoothness, EdgeAwareSmoothnessMulti, EdgeConfig, FeatConfig, FeatureMetricLoss, MaskedReconstructionLoss,
                   PhotoConfig, PhotometricSmoothLoss)
 
 
@@ -164,10 +164,24 @@ class ViewSynthesisLossMixin:
                 k += 1
         return losses
 
+    def _refuse_silent_no_grad(self, what, tensors):
+        """The stand-alone ``generate_*_pred`` calls return tensors WITHOUT autograd history (the fused kernels own the
+        backward of the loss, not of the warped tensors).  The reference's versions are differentiable; a caller that
+        builds its own loss term on them (as mono/model/mono_fm_joint_im_rot/net.py:53-133 does) would silently train
+        nothing -- so that case is an error, not a silent no-op."""
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+            raise RuntimeError(
+                f"{what}: the stand-alone call returns warped tensors without autograd history, but its inputs require "
+                "grad.  Gradients of the view-synthesis losses flow through compute_losses(); call this method under "
+                "torch.no_grad() if the warped tensors are only inspected (visualisation, metrics), or build the extra "
+                "loss term from compute_losses' entries.")
+
     def generate_images_pred(self, inputs, outputs, scale):
-        """mono/model/mono_fm/net.py:157-170.  Stand-alone use warps the sources for ONE scale;
-        the images are produced by the fused kernel and carry no autograd history (gradients
-        flow through compute_losses)."""
+        """mono/model/mono_fm/net.py:157-170.  Stand-alone use warps the sources for ONE scale; the images are produced by
+        the fused kernel and carry no autograd history (gradients flow through compute_losses) -- see
+        _refuse_silent_no_grad for what happens when a caller would need them to."""
+        self._refuse_silent_no_grad("generate_images_pred", [outputs[("disp", 0, scale)]] +
+                                    [self._pose(inputs, outputs, f) for f in self._src_frames()])
         with torch.no_grad():
             self._photometric(inputs, outputs, [scale], materialize=True)
         return outputs
@@ -196,6 +210,9 @@ class ViewSynthesisLossMixin:
 
     def generate_features_pred(self, inputs, outputs):
         """mono/model/mono_fm/net.py:172-199 (stand-alone: warped features, no autograd history)."""
+        self._refuse_silent_no_grad("generate_features_pred", [outputs[("disp", 0, 0)]] +
+                                    [self._pose(inputs, outputs, f) for f in self._src_frames()] +
+                                    list(getattr(self, "extractor", None).parameters() if hasattr(self, "extractor") else []))
         with torch.no_grad():
             src = {f: self._extract(inputs[("color", f, 0)]) for f in self._src_frames()}
             tgt = self._extract(inputs[("color", 0, 0)])
@@ -266,9 +283,7 @@ class ViewSynthesisLossMixin:
         n = len(scales)
         target = inputs[("color", 0, 0)]
         loss_dict = LossDict()
-        for i in range(5):
-            loss_dict[("feature_regularization_loss", i)] = self.get_feature_regularization_loss(
-                features[i], target) / (2 ** i) / 5
+        self._feature_regularization(loss_dict, features, target)
         if src_fs is None:
             src_fs = {f: self._extract(inputs[("color", f, 0)]) for f in self._src_frames()}
         per, idx = self._feature_metric(inputs, outputs, features[0], src_fs, opt.perception_weight / n)
@@ -282,7 +297,7 @@ class ViewSynthesisLossMixin:
             loss_dict[("smooth_loss", s)] = base[("smooth_loss", s)]
             if idx is not None:
                 outputs[("min_index", s)] = idx        # the reference overwrites the photometric map (net.py:142)
-        loss_dict._parts = list(base._parts)
+        loss_dict._parts += base._parts
         loss_dict.add_part(per, n, [("min_perceptional_loss", s) for s in scales])
         return loss_dict
 
@@ -294,9 +309,7 @@ class ViewSynthesisLossMixin:
         loss_dict = LossDict()
         target = inputs[("color", 0, 0)]
         if features is not None:
-            for i in range(5):
-                loss_dict[("feature_regularization_loss", i)] = self.get_feature_regularization_loss(
-                    features[i], target) / (2 ** i) / 5
+            self._feature_regularization(loss_dict, features, target)
             if src_fs is None:
                 src_fs = {f: self._extract(inputs[("color", f, 0)]) for f in self._src_frames()}
             per, idx = self._feature_metric(inputs, outputs, features[0], src_fs, opt.perception_weight)
@@ -327,6 +340,17 @@ class ViewSynthesisLossMixin:
             l1 = torch.sqrt(torch.pow(res - target, 2) + 1e-3 ** 2).mean(1, True)
             loss_dict["auto_res_loss"] = l1 * self.opt.auto_res_weight
         return loss_dict
+
+    def _feature_regularization(self, loss_dict, features, target, n_levels=5):
+        """('feature_regularization_loss', i) = get_feature_regularization_loss(features[i], target) / 2**i / 5 for the five
+        encoder levels (mono/model/mono_fm_joint/net.py:77-80), all levels in one multi-level call: the per-level factor is
+        folded into the coefficients, so every entry is a view of one kernel-written vector."""
+        cfgs = tuple(EdgeConfig(alpha=1.0, first_coef=-float(self.opt.dis) / (2 ** i) / n_levels,
+                                second_coef=float(self.opt.cvt) / (2 ** i) / n_levels) for i in range(n_levels))
+        reg = EdgeAwareSmoothnessMulti.apply(cfgs, target, *features[:n_levels])
+        for i in range(n_levels):
+            loss_dict[("feature_regularization_loss", i)] = reg[i]
+        loss_dict.add_part(reg, 1, [("feature_regularization_loss", i) for i in range(n_levels)])
 
     def get_feature_regularization_loss(self, feature, img):
         """mono/model/mono_fm_joint/net.py:309-330: -dis * first-order + cvt * second-order."""

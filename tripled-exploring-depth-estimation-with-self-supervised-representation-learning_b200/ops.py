@@ -13,7 +13,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import EdgeArgs, FeatArgs, PhotoArgs, PoseArgs, ReconArgs, TDL_MAX_SCALES, TDL_MAX_SRC
+from ._lib import EdgeArgs, EdgeMultiArgs, FeatArgs, PhotoArgs, PoseArgs, ReconArgs, TDL_MAX_LEVELS, TDL_MAX_SCALES, TDL_MAX_SRC
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -356,6 +356,58 @@ class EdgeAwareSmoothness(torch.autograd.Function):
         with torch.cuda.device(feature.device):
             _lib.check(L.tdl_edge_smooth_bwd(C.byref(a), _stream()), "tdl_edge_smooth_bwd")
         return None, d_feat, None
+
+
+class EdgeAwareSmoothnessMulti(torch.autograd.Function):
+    """get_feature_regularization_loss on ALL encoder levels in one call (the reference loops over five levels,
+    mono/model/mono_fm_joint/net.py:77-80): forward(cfgs (EdgeConfig per level), image (B,3,H,W), *features) ->
+    losses[n_levels].  Three launches forward, one backward, whatever the number of levels."""
+
+    @staticmethod
+    def forward(ctx, cfgs, image, *features):
+        L = _lib.lib()
+        n = len(features)
+        if not 1 <= n <= TDL_MAX_LEVELS or len(cfgs) != n:
+            raise _lib.TdlError(f"expected 1..{TDL_MAX_LEVELS} feature levels with one EdgeConfig each")
+        image = _f32c(image, "image")
+        feats = [_f32c(f, "feature") for f in features]
+        losses = torch.empty(n, dtype=torch.float32, device=image.device)
+        m, keep = EdgeAwareSmoothnessMulti._args(L, cfgs, feats, image, losses, None)
+        with torch.cuda.device(image.device):
+            _lib.check(L.tdl_edge_smooth_multi_fwd(C.byref(m), _stream()), "tdl_edge_smooth_multi_fwd")
+        ctx.cfgs = cfgs
+        ctx.save_for_backward(image, *feats, *keep)
+        return losses
+
+    @staticmethod
+    def _args(L, cfgs, feats, image, losses, wss):
+        m = EdgeMultiArgs()
+        m.nlevels = len(feats)
+        keep = []
+        for l, (cfg, f) in enumerate(zip(cfgs, feats)):
+            a, ws = EdgeAwareSmoothness._args(L, cfg, f, image, None if wss is None else wss[l])
+            a.loss = losses[l:l + 1].data_ptr()
+            m.level[l] = a
+            keep.append(ws)
+        return m, keep
+
+    @staticmethod
+    def backward(ctx, g_losses):
+        L = _lib.lib()
+        n = len(ctx.cfgs)
+        image = ctx.saved_tensors[0]
+        feats = ctx.saved_tensors[1:1 + n]
+        wss = ctx.saved_tensors[1 + n:1 + 2 * n]
+        scratch = torch.empty(n, dtype=torch.float32, device=image.device)
+        m, _ = EdgeAwareSmoothnessMulti._args(L, ctx.cfgs, feats, image, scratch, wss)
+        g_losses = _f32c(g_losses, "grad")
+        d_feats = [torch.empty_like(f) for f in feats]
+        for l in range(n):
+            m.level[l].dloss = g_losses[l:l + 1].data_ptr()
+            m.level[l].d_feature = d_feats[l].data_ptr()
+        with torch.cuda.device(image.device):
+            _lib.check(L.tdl_edge_smooth_multi_bwd(C.byref(m), _stream()), "tdl_edge_smooth_multi_bwd")
+        return (None, None, *d_feats)
 
 
 # --------------------------------------------------------------------------------------------------
