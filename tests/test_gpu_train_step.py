@@ -117,6 +117,7 @@ def test_two_rank_gradients_equal_single_gpu_on_the_concatenated_batch(tmp_path)
     mp.spawn(_rank_main, args=(2, port, backend, str(tmp_path)), nprocs=2, join=True)
     dist_grad = torch.load(os.path.join(str(tmp_path), "dist_grad.pt"))
     dev = "cuda"
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     model = _model(tdl, 4, dev, True)
@@ -124,6 +125,5 @@ def test_two_rank_gradients_equal_single_gpu_on_the_concatenated_batch(tmp_path)
     model(_inputs(tdl, 4, dev))[1].total().backward()
     single = step.flat_grad.cpu()
     err = float((dist_grad - single).norm() / single.norm())
-    torch.backends.cudnn.allow_tf32 = True
-    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
     assert err < 1e-4, (backend, err)

@@ -93,6 +93,17 @@ def test_generate_images_pred_standalone():
         net.generate_images_pred(inputs, outputs, 2)
 
 
+def test_projection_is_full_fp32_under_tf32_matmul():
+    """Training scripts switch TF32 matmuls on for the networks; the 3x4 projection matrices must not inherit that."""
+    rec = _synthetic_record("baseline", 1, 64, 96, 0, 2007, frames="waves")
+    saved = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        _check(rec, "baseline-tf32-matmul-flag")
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = saved
+
+
 def test_reference_noise_mode_reproduces_reference_rng_stream():
     """noise_mode='reference' draws torch.randn from the global CPU generator in the reference's order."""
     rec = _synthetic_record("baseline", 1, 64, 96, 0, 2006, frames="smooth")
