@@ -89,9 +89,12 @@ __global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) 
         }
     }
     __syncwarp();
-    // ---- phase 2: two pixels per step, one half-warp each.  Every row of a pixel (target + 4 taps per source frame) is
-    //      requested before the first use, and the rows of the NEXT pixel are requested before the arithmetic of the current
-    //      one (the stores of the warped rows would otherwise fence the loads: the pointers may alias for the compiler)
+    // ---- phase 2: two pixels per step, one half-warp each.  The rows of a step (target + 4 taps per source frame, 16 or
+    //      8 bytes per lane and row) travel global -> shared memory with cp.async, kStages steps ahead of the arithmetic:
+    //      the kernel was bound by the latency of these loads with one step of register prefetch (41 % of the stall
+    //      samples on the first use of a row, 22 % warps active at 126 registers), and data in flight in shared memory
+    //      costs no registers.  Each lane reads back exactly the bytes it copied, so no barrier is needed -- only the
+    //      cp.async group wait.
     const T* __restrict__ tgt = reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C;
     const T* __restrict__ srcb[S];
     T* __restrict__ wrpb[S];
@@ -100,13 +103,27 @@ __global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) 
         srcb[f] = reinterpret_cast<const T*>(p.src[f]) + (size_t)b * hw * C;
         wrpb[f] = p.warped[f] ? reinterpret_cast<T*>(p.warped[f]) + (size_t)b * hw * C : nullptr;
     }
-    struct Rows {
-        float4 t, v[S][4];
-        float wgt[S][4];
+    constexpr int kStages = 3;
+    constexpr int kRowsPerStep = 1 + 4 * S;
+    constexpr int kLaneBytes = 4 * (int)sizeof(T);          // 16 (fp32) or 8 (bf16) bytes per lane and row
+    extern __shared__ __align__(16) unsigned char s_ring_raw[];
+    // ring[warp][stage][row][lane]
+    unsigned char* ring = s_ring_raw + (size_t)wq * kStages * kRowsPerStep * 32 * kLaneBytes;
+    auto slot = [&](int stage, int row) { return ring + ((size_t)(stage * kRowsPerStep + row) * 32 + lane) * kLaneBytes; };
+    auto cp_async = [&](void* dst, const void* src) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+        if (kLaneBytes == 16)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+        else
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
     };
-    auto fetch = [&](int pl, int c, Rows& r) {
+    const int nchunk = (C + 63) / 64;                       // 64-channel chunks; lanes past C redo the last quad (not used)
+    const int cl = 4 * l16;
+    auto issue = [&](int q, int ck, int stage) {
+        const int pl = q + half;
         const int pix = min(pix0 + pl, hw - 1);
-        r.t = ld4(tgt + (size_t)pix * C + c);
+        const int c = min(cl + 64 * ck, C - 4);
+        cp_async(slot(stage, 0), tgt + (size_t)pix * C + c);
 #pragma unroll
         for (int f = 0; f < S; ++f) {
             const Tap tp = s_tap[wq][pl][f];
@@ -114,62 +131,77 @@ __global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) 
             const int dx = (tp.o00 >> 30) & 1, dy = ((tp.o00 >> 29) & 1) ? w : 0;
             // a clamped tap has weight exactly 0, so loading the clamped row adds 0 like ATen's skipped tap
             const T* sb = srcb[f] + c;
-            r.v[f][0] = ld4(sb + (size_t)o * C);
-            r.v[f][1] = ld4(sb + (size_t)(o + dx) * C);
-            r.v[f][2] = ld4(sb + (size_t)(o + dy) * C);
-            r.v[f][3] = ld4(sb + (size_t)(o + dy + dx) * C);
-            r.wgt[f][0] = tp.nw;
-            r.wgt[f][1] = tp.ne;
-            r.wgt[f][2] = tp.sw;
-            r.wgt[f][3] = tp.se;
+            cp_async(slot(stage, 1 + 4 * f + 0), sb + (size_t)o * C);
+            cp_async(slot(stage, 1 + 4 * f + 1), sb + (size_t)(o + dx) * C);
+            cp_async(slot(stage, 1 + 4 * f + 2), sb + (size_t)(o + dy) * C);
+            cp_async(slot(stage, 1 + 4 * f + 3), sb + (size_t)(o + dy + dx) * C);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    const int nchunk = (C + 63) / 64;                       // 64-channel chunks; lanes past C idle in the last one
-    const int nsteps = (PIX / 2) * nchunk;
-    const int cl = 4 * l16;
+    auto rd = [&](int stage, int row) -> float4 {
+        const unsigned char* q = slot(stage, row);
+        if (sizeof(T) == 4) return *reinterpret_cast<const float4*>(q);
+        const uint2 u = *reinterpret_cast<const uint2*>(q);
+        return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                           __uint_as_float(u.y & 0xffff0000u));
+    };
     float acc[S];
 #pragma unroll
     for (int f = 0; f < S; ++f) acc[f] = 0.f;
-    // one step: request the rows of step it+1 into `nxt`, then consume `cur` (requested one step earlier).  Two register
-    // sets alternate (no copy between them: a copy would wait for the loads it is meant to overlap)
-    auto step = [&](int it, Rows& cur, Rows& nxt) {
-        const int q = (it / nchunk) * 2, ck = it - (it / nchunk) * nchunk;
-        const int pl = q + half, c = cl + 64 * ck;
-        const int pix = pix0 + pl;
-        if (it + 1 < nsteps) {
-            const int q2 = ((it + 1) / nchunk) * 2, ck2 = (it + 1) - ((it + 1) / nchunk) * nchunk;
-            fetch(q2 + half, min(cl + 64 * ck2, C - 4), nxt);
-        }
-        if (pix < hw && c < C) {
-#pragma unroll
-            for (int f = 0; f < S; ++f) {
-                float4 v;
-                v.x = cur.v[f][0].x * cur.wgt[f][0] + cur.v[f][1].x * cur.wgt[f][1] + cur.v[f][2].x * cur.wgt[f][2] + cur.v[f][3].x * cur.wgt[f][3];
-                v.y = cur.v[f][0].y * cur.wgt[f][0] + cur.v[f][1].y * cur.wgt[f][1] + cur.v[f][2].y * cur.wgt[f][2] + cur.v[f][3].y * cur.wgt[f][3];
-                v.z = cur.v[f][0].z * cur.wgt[f][0] + cur.v[f][1].z * cur.wgt[f][1] + cur.v[f][2].z * cur.wgt[f][2] + cur.v[f][3].z * cur.wgt[f][3];
-                v.w = cur.v[f][0].w * cur.wgt[f][0] + cur.v[f][1].w * cur.wgt[f][1] + cur.v[f][2].w * cur.wgt[f][2] + cur.v[f][3].w * cur.wgt[f][3];
-                if (wrpb[f]) st4(wrpb[f] + (size_t)pix * C + c, v);
-                const float e0 = v.x - cur.t.x, e1 = v.y - cur.t.y, e2 = v.z - cur.t.z, e3 = v.w - cur.t.w;      // robust_l1(tgt_f, src_f)
-                acc[f] += sqrt_fast(fmaf(e0, e0, kL1Eps2)) + sqrt_fast(fmaf(e1, e1, kL1Eps2)) +
-                          sqrt_fast(fmaf(e2, e2, kL1Eps2)) + sqrt_fast(fmaf(e3, e3, kL1Eps2));
-            }
-        }
-        if (ck == nchunk - 1) {                              // last chunk of this pixel pair: reduce over the 16 lanes
-#pragma unroll
-            for (int f = 0; f < S; ++f) {
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], o);
-                if (l16 == 0) s_res[wq][pl][f] = acc[f];
-                acc[f] = 0.f;
-            }
+    // prologue: the first kStages - 1 steps are requested
+    int iq = 0, ick = 0;                                     // (pixel pair, chunk) of the next step to request
+    auto advance = [&](int& q, int& ck) {
+        if (++ck == nchunk) {
+            ck = 0;
+            q += 2;
         }
     };
-    {
-        Rows ra, rb;
-        fetch(half, min(cl, C - 4), ra);
-        for (int it = 0; it < nsteps; it += 2) {             // nsteps is even (PIX / 2 = 16 pixel pairs)
-            step(it, ra, rb);
-            step(it + 1, rb, ra);
+#pragma unroll
+    for (int k = 0; k < kStages - 1; ++k) {
+        if (iq < PIX) issue(iq, ick, k);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        advance(iq, ick);
+    }
+    int stage = 0;
+    for (int q = 0; q < PIX; q += 2) {
+        const int pl = q + half;
+        const int pix = pix0 + pl;
+        for (int ck = 0; ck < nchunk; ++ck) {
+            // request step + (kStages - 1) into the slot consumed in the previous iteration, then wait for this step's group
+            {
+                const int st_next = stage == 0 ? kStages - 1 : stage - 1;
+                if (iq < PIX) issue(iq, ick, st_next);
+                else asm volatile("cp.async.commit_group;" ::: "memory");
+                advance(iq, ick);
+            }
+            asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
+            const int c = cl + 64 * ck;
+            if (pix < hw && c < C) {
+                const float4 t = rd(stage, 0);
+#pragma unroll
+                for (int f = 0; f < S; ++f) {
+                    const Tap tp = s_tap[wq][pl][f];
+                    const float4 a = rd(stage, 1 + 4 * f), bq = rd(stage, 2 + 4 * f), cq = rd(stage, 3 + 4 * f), d = rd(stage, 4 + 4 * f);
+                    float4 v;
+                    v.x = a.x * tp.nw + bq.x * tp.ne + cq.x * tp.sw + d.x * tp.se;
+                    v.y = a.y * tp.nw + bq.y * tp.ne + cq.y * tp.sw + d.y * tp.se;
+                    v.z = a.z * tp.nw + bq.z * tp.ne + cq.z * tp.sw + d.z * tp.se;
+                    v.w = a.w * tp.nw + bq.w * tp.ne + cq.w * tp.sw + d.w * tp.se;
+                    if (wrpb[f]) st4(wrpb[f] + (size_t)pix * C + c, v);
+                    const float e0 = v.x - t.x, e1 = v.y - t.y, e2 = v.z - t.z, e3 = v.w - t.w;      // robust_l1(tgt_f, src_f)
+                    acc[f] += sqrt_fast(fmaf(e0, e0, kL1Eps2)) + sqrt_fast(fmaf(e1, e1, kL1Eps2)) +
+                              sqrt_fast(fmaf(e2, e2, kL1Eps2)) + sqrt_fast(fmaf(e3, e3, kL1Eps2));
+                }
+            }
+            stage = stage + 1 == kStages ? 0 : stage + 1;
+        }
+        // all chunks of this pixel pair done: reduce over the 16 lanes
+#pragma unroll
+        for (int f = 0; f < S; ++f) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], o);
+            if (l16 == 0) s_res[wq][pl][f] = acc[f];
+            acc[f] = 0.f;
         }
     }
     __syncwarp();
@@ -492,18 +524,27 @@ __global__ void __launch_bounds__(256) feat_overflow_nhwc_kernel(const FeatDev p
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+template <int S, typename T>
+static cudaError_t fwd_st(const FeatDev& p, cudaStream_t st) {
+    using namespace f2;
+    // cp.async ring: 3 stages x (1 + 4S) rows x 32 lanes x (16 | 8) bytes per warp
+    const size_t smem = (size_t)(NT / 32) * 3 * (1 + 4 * S) * 32 * 4 * sizeof(T);
+    static SmemOptIn opt_in;
+    if (cudaError_t e = opt_in(feat_fwd_nhwc_kernel<S, T>, smem)) return e;
+    dim3 grid((unsigned)((p.h * p.w + NT - 1) / NT), p.B);
+    feat_fwd_nhwc_kernel<S, T><<<grid, NT, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 template <typename T>
 static cudaError_t fwd_t(const FeatDev& p, cudaStream_t st) {
-    using namespace f2;
-    dim3 grid((unsigned)((p.h * p.w + NT - 1) / NT), p.B);
     switch (p.S) {
-        case 1: feat_fwd_nhwc_kernel<1, T><<<grid, NT, 0, st>>>(p); break;
-        case 2: feat_fwd_nhwc_kernel<2, T><<<grid, NT, 0, st>>>(p); break;
-        case 3: feat_fwd_nhwc_kernel<3, T><<<grid, NT, 0, st>>>(p); break;
-        case 4: feat_fwd_nhwc_kernel<4, T><<<grid, NT, 0, st>>>(p); break;
-        default: return cudaErrorInvalidValue;
+        case 1: return fwd_st<1, T>(p, st);
+        case 2: return fwd_st<2, T>(p, st);
+        case 3: return fwd_st<3, T>(p, st);
+        case 4: return fwd_st<4, T>(p, st);
     }
-    return cudaGetLastError();
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_feat_fwd_nhwc(const FeatDev& p, cudaStream_t st) {
