@@ -28,6 +28,8 @@
  *       get_feature_regularization_loss mono/model/mono_fm_joint/net.py:309-330 (called per level at :77-80)
  *   tdl_recon_fwd / tdl_recon_bwd
  *       masked img_reconstruct_loss     mono/model/mono_fm_joint_inpaint/net.py:80-91
+ *   tdl_proj_fwd / tdl_proj_bwd
+ *       K @ T, K/2 and its inverse      mono/model/mono_fm/layers.py:58,74; mono/model/mono_fm/net.py:185-191
  *   tdl_pose_fwd / tdl_pose_bwd
  *       transformation_from_parameters  mono/model/mono_fm/net.py:201-212 (get_translation_matrix :214-222,
  *                                       rot_from_axisangle :224-253), called by predict_poses (net.py:142-155)
@@ -211,6 +213,30 @@ typedef struct tdl_pose_args {
     float* d_translation;       /* out (B,3), overwritten                                                   */
 } tdl_pose_args;
 
+/* ------------------------------------------------------------------ projection prologue (K, inv_K, cam_T_cam -> P, inv_K 3x3) */
+/* Everything the loss kernels need from the camera matrices, in one launch each way:
+ *   P_full[b][f] = (K @ T_f)[:3, :]                      Project.forward                 mono/model/mono_fm/layers.py:74
+ *   P_half[b][f] = (K' @ T_f)[:3, :], K' = K with rows 0, 1 halved   generate_features_pred   mono/model/mono_fm/net.py:185-187
+ *   invK3        = inv_K[:, :3, :3]                      Backproject.forward             mono/model/mono_fm/layers.py:58
+ *   invKh3       = pinv(K')[:, :3, :3] = inv_K[:, :3, :3] with columns 0, 1 doubled      mono/model/mono_fm/net.py:188-191
+ * (the reference spends a matmul, a slice and -- per frame, per scale -- a clone, two divisions and a per-sample SVD on
+ * these 12 + 9 numbers per image; eager PyTorch needs ~30 small kernels for them forward + backward).  Full fp32
+ * whatever torch's TF32 matmul switch says.  Backward: dT_f = K[:3]^T (dP_full_f + diag(1/2, 1/2, 1) dP_half_f). */
+typedef struct tdl_proj_args {
+    int32_t B, S;
+    const float* K;                      /* (B,4,4) inputs["K"]                                           */
+    const float* inv_K;                  /* (B,4,4) inputs["inv_K"]                                       */
+    const float* T[TDL_MAX_SRC];         /* (B,4,4) cam_T_cam (or stereo_T) of every source frame         */
+    float* P_full;                       /* out (B,S,3,4)                                                 */
+    float* P_half;                       /* out (B,S,3,4)                                                 */
+    float* invK3;                        /* out (B,3,3)                                                   */
+    float* invKh3;                       /* out (B,3,3)                                                   */
+    /* backward only */
+    const float* dP_full;                /* (B,S,3,4) or NULL (treated as zero)                           */
+    const float* dP_half;                /* (B,S,3,4) or NULL                                             */
+    float* dT[TDL_MAX_SRC];              /* out (B,4,4) per frame, overwritten; NULL entries are skipped  */
+} tdl_proj_args;
+
 int tdl_abi_version(void);
 const char* tdl_strerror(int code);
 /* Process-wide switches for tests and kernel experiments (the defaults are the product path).  They are
@@ -249,6 +275,9 @@ int tdl_recon_bwd(const tdl_recon_args* args, tdl_stream_t stream);
 
 int tdl_pose_fwd(const tdl_pose_args* args, tdl_stream_t stream);
 int tdl_pose_bwd(const tdl_pose_args* args, tdl_stream_t stream);
+
+int tdl_proj_fwd(const tdl_proj_args* args, tdl_stream_t stream);
+int tdl_proj_bwd(const tdl_proj_args* args, tdl_stream_t stream);
 
 #ifdef __cplusplus
 }

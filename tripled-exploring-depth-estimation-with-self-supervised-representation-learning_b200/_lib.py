@@ -88,6 +88,15 @@ class PoseArgs(C.Structure):
     ]
 
 
+class ProjArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("S", C.c_int32),
+        ("K", _vp), ("inv_K", _vp), ("T", _vp * TDL_MAX_SRC),
+        ("P_full", _vp), ("P_half", _vp), ("invK3", _vp), ("invKh3", _vp),
+        ("dP_full", _vp), ("dP_half", _vp), ("dT", _vp * TDL_MAX_SRC),
+    ]
+
+
 class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int32), ("total_ms", C.c_double)]
 
@@ -96,7 +105,8 @@ EXPORTS = ["tdl_abi_version", "tdl_strerror", "tdl_set_option", "tdl_get_option"
            "tdl_photo_ws_bytes", "tdl_photo_fwd", "tdl_photo_bwd",
            "tdl_feat_ws_bytes", "tdl_feat_bwd_scratch_bytes", "tdl_feat_fwd", "tdl_feat_bwd",
            "tdl_edge_ws_bytes", "tdl_edge_smooth_fwd", "tdl_edge_smooth_bwd", "tdl_edge_smooth_multi_fwd", "tdl_edge_smooth_multi_bwd",
-           "tdl_recon_ws_bytes", "tdl_recon_fwd", "tdl_recon_bwd", "tdl_pose_fwd", "tdl_pose_bwd"]
+           "tdl_recon_ws_bytes", "tdl_recon_fwd", "tdl_recon_bwd", "tdl_pose_fwd", "tdl_pose_bwd",
+           "tdl_proj_fwd", "tdl_proj_bwd"]
 
 _lib = None
 
@@ -141,7 +151,8 @@ def lib():
                     ("tdl_edge_smooth_fwd", EdgeArgs), ("tdl_edge_smooth_bwd", EdgeArgs),
                     ("tdl_edge_smooth_multi_fwd", EdgeMultiArgs), ("tdl_edge_smooth_multi_bwd", EdgeMultiArgs),
                     ("tdl_recon_fwd", ReconArgs), ("tdl_recon_bwd", ReconArgs),
-                    ("tdl_pose_fwd", PoseArgs), ("tdl_pose_bwd", PoseArgs)):
+                    ("tdl_pose_fwd", PoseArgs), ("tdl_pose_bwd", PoseArgs),
+                    ("tdl_proj_fwd", ProjArgs), ("tdl_proj_bwd", ProjArgs)):
         fn = getattr(L, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(T), C.c_void_p]

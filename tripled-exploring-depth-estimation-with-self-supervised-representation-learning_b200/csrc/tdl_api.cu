@@ -278,6 +278,7 @@ int tdl_launch_count(const char* entry) {
     if (!strcmp(entry, "tdl_recon_fwd")) return 2;        // recon_fwd, finalize
     if (!strcmp(entry, "tdl_recon_bwd")) return 1;
     if (!strcmp(entry, "tdl_pose_fwd") || !strcmp(entry, "tdl_pose_bwd")) return 1;
+    if (!strcmp(entry, "tdl_proj_fwd") || !strcmp(entry, "tdl_proj_bwd")) return 1;
     return 0;
 }
 
@@ -673,6 +674,29 @@ int tdl_pose_bwd(const tdl_pose_args* a, tdl_stream_t stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("pose_bwd", launch_pose_bwd(a->axisangle, a->translation, a->dT, a->B, a->invert, a->d_axisangle,
                                            a->d_translation, st));
+    return TDL_OK;
+}
+
+// ------------------------------------------------------------------------------------ projection prologue
+int tdl_proj_fwd(const tdl_proj_args* a, tdl_stream_t stream) {
+    if (!a || !a->K || !a->inv_K || !a->P_full || !a->P_half || !a->invK3 || !a->invKh3) return TDL_ERR_NULL;
+    if (a->S < 1 || a->S > TDL_MAX_SRC) return TDL_ERR_COUNT;
+    if (a->B < 1) return TDL_ERR_SHAPE;
+    for (int f = 0; f < a->S; ++f)
+        if (!a->T[f]) return TDL_ERR_NULL;
+    if (const int rc = check_device()) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDL_KERNEL("proj_fwd", launch_proj_fwd(*a, st));
+    return TDL_OK;
+}
+
+int tdl_proj_bwd(const tdl_proj_args* a, tdl_stream_t stream) {
+    if (!a || !a->K) return TDL_ERR_NULL;
+    if (a->S < 1 || a->S > TDL_MAX_SRC) return TDL_ERR_COUNT;
+    if (a->B < 1) return TDL_ERR_SHAPE;
+    if (const int rc = check_device()) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TDL_KERNEL("proj_bwd", launch_proj_bwd(*a, st));
     return TDL_OK;
 }
 

@@ -166,6 +166,8 @@ cudaError_t launch_feat_overflow_nhwc(const FeatDev& p, cudaStream_t st);
 cudaError_t launch_edge_finalize(const double* acc, int acc_stride, int B, float first_coef, float second_coef,
                                  int h, int w, float* loss, cudaStream_t st);
 
+cudaError_t launch_proj_fwd(const tdl_proj_args& a, cudaStream_t st);
+cudaError_t launch_proj_bwd(const tdl_proj_args& a, cudaStream_t st);
 cudaError_t launch_pose_fwd(const float* aa, const float* tr, int B, int invert, float* T, cudaStream_t st);
 cudaError_t launch_pose_bwd(const float* aa, const float* tr, const float* dT, int B, int invert, float* d_aa, float* d_tr,
                             cudaStream_t st);

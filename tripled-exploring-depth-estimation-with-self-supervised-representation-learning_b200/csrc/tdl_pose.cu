@@ -142,4 +142,82 @@ cudaError_t launch_pose_bwd(const float* aa, const float* tr, const float* dT, i
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Projection prologue (include/tdl.h tdl_proj_args): one thread per output element.
+struct ProjDev {
+    int B, S;
+    const float* K;
+    const float* inv_K;
+    const float* T[TDL_MAX_SRC];
+    float* P_full;
+    float* P_half;
+    float* invK3;
+    float* invKh3;
+    const float* dP_full;
+    const float* dP_half;
+    float* dT[TDL_MAX_SRC];
+};
+
+__global__ void proj_fwd_kernel(const ProjDev p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nP = p.B * p.S * 12;
+    if (i < nP) {
+        const int c = i & 3, r = (i >> 2) % 3, f = (i / 12) % p.S, b = i / (12 * p.S);
+        const float* K = p.K + (size_t)b * 16 + r * 4;
+        const float* T = p.T[0];
+#pragma unroll
+        for (int q = 1; q < TDL_MAX_SRC; ++q)
+            if (q == f) T = p.T[q];
+        T += (size_t)b * 16 + c;
+        float acc = __fmul_rn(K[0], T[0]);                    // k = 0..3 in order, one rounding per term like a fp32 matmul
+        acc = fmaf(K[1], T[4], acc);
+        acc = fmaf(K[2], T[8], acc);
+        acc = fmaf(K[3], T[12], acc);
+        p.P_full[i] = acc;
+        p.P_half[i] = r < 2 ? 0.5f * acc : acc;               // (K/2) @ T == (K @ T)/2 exactly: a power-of-two scale
+    } else if (i < nP + p.B * 9) {
+        const int j = i - nP, c = j % 3, r = (j / 3) % 3, b = j / 9;
+        const float v = p.inv_K[(size_t)b * 16 + r * 4 + c];
+        p.invK3[j] = v;
+        p.invKh3[j] = c < 2 ? 2.f * v : v;                    // pinv(diag(1/2,1/2,1,1) K) = pinv(K) diag(2,2,1,1)
+    }
+}
+
+__global__ void proj_bwd_kernel(const ProjDev p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.B * p.S * 16) return;
+    const int c = i & 3, k = (i >> 2) & 3, f = (i / 16) % p.S, b = i / (16 * p.S);
+    float* dT = p.dT[0];
+#pragma unroll
+    for (int q = 1; q < TDL_MAX_SRC; ++q)
+        if (q == f) dT = p.dT[q];
+    if (!dT) return;
+    const float* K = p.K + (size_t)b * 16;
+    const size_t o = ((size_t)b * p.S + f) * 12 + c;
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float g = p.dP_full ? p.dP_full[o + r * 4] : 0.f;
+        if (p.dP_half) g += (r < 2 ? 0.5f : 1.f) * p.dP_half[o + r * 4];
+        acc = fmaf(K[r * 4 + k], g, acc);
+    }
+    dT[(size_t)b * 16 + k * 4 + c] = acc;
+}
+
+cudaError_t launch_proj_fwd(const tdl_proj_args& a, cudaStream_t st) {
+    ProjDev p{a.B, a.S, a.K, a.inv_K, {a.T[0], a.T[1], a.T[2], a.T[3]}, a.P_full, a.P_half, a.invK3, a.invKh3, nullptr, nullptr,
+              {nullptr, nullptr, nullptr, nullptr}};
+    const int n = a.B * a.S * 12 + a.B * 9;
+    proj_fwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_proj_bwd(const tdl_proj_args& a, cudaStream_t st) {
+    ProjDev p{a.B, a.S, a.K, a.inv_K, {nullptr, nullptr, nullptr, nullptr}, nullptr, nullptr, nullptr, nullptr, a.dP_full, a.dP_half,
+              {a.dT[0], a.dT[1], a.dT[2], a.dT[3]}};
+    const int n = a.B * a.S * 16;
+    proj_bwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
 }  // namespace tdl

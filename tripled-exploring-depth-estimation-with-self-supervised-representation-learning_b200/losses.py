@@ -31,7 +31,7 @@ import torch
 from .geometry import half_res_intrinsics, projection_matrix
 import torch.nn.functional as F
 
-from .ops import (EdgeAwareSmoothness, EdgeAwareSmoothnessMulti, EdgeConfig, FeatConfig, FeatureMetricLoss, MaskedReconstructionLoss,
+from .ops import (projection_prologue, EdgeAwareSmoothness, EdgeAwareSmoothnessMulti, EdgeConfig, FeatConfig, FeatureMetricLoss, MaskedReconstructionLoss,
                   PhotoConfig, PhotometricSmoothLoss)
 
 
@@ -117,6 +117,25 @@ class ViewSynthesisLossMixin:
     def _stack_P(self, inputs, outputs, K):
         return torch.stack([projection_matrix(K, self._pose(inputs, outputs, f)) for f in self._src_frames()], 1)
 
+    def _camera(self, inputs, outputs):
+        """(P_full, P_half, invK3, invKh3) for this call: ONE launch (tdl_proj_fwd) instead of ~15 small PyTorch kernels
+        (matmul / slice / stack per frame, clone + scale of K and inv_K for the half-resolution feature path), and one
+        instead of ~15 in the backward.  Cached on the outputs dict so that the photometric and the feature-metric term of
+        one step share it."""
+        Ts = [self._pose(inputs, outputs, f) for f in self._src_frames()]
+        key = tuple((t.data_ptr(), t._version) for t in Ts + [inputs["K"], inputs["inv_K"]])
+        cached = outputs.get("_tdl_camera")
+        cam = cached[1] if cached is not None and cached[0] == key else None
+        if cam is None:
+            if inputs["K"].is_cuda:
+                cam = projection_prologue(inputs["K"], inputs["inv_K"], Ts)
+            else:                                   # (CPU tensors only reach this in host-logic tests; the kernels refuse them later)
+                Kh, invKh = half_res_intrinsics(inputs["K"], inputs.get("inv_K"))
+                cam = (self._stack_P(inputs, outputs, inputs["K"]), self._stack_P(inputs, outputs, Kh),
+                       inputs["inv_K"][:, :3, :3], invKh[:, :3, :3].contiguous())
+            outputs["_tdl_camera"] = (key, cam)
+        return cam
+
     def _reference_noise(self, scales, batch, device):
         H, W = self.opt.height, self.opt.width
         return {s: {f: torch.randn(batch, 1, H, W).to(device, non_blocking=True) for f in self._src_frames()}
@@ -145,8 +164,7 @@ class ViewSynthesisLossMixin:
             materialize=self.materialize_outputs if materialize is None else materialize,
             noise_seed=(torch.initial_seed() * 1000003 + step) & (2 ** 63 - 1),
             has_noise=noise is not None and bool(opt.automask))
-        P = self._stack_P(inputs, outputs, inputs["K"])
-        invK = inputs["inv_K"][:, :3, :3]
+        P, _, invK, _ = self._camera(inputs, outputs)
         tensors = [inputs[("color", f, 0)] for f in frames] + [outputs[("disp", 0, s)] for s in scales]
         if cfg.has_noise:
             tensors += [noise[s][f] for s in scales for f in frames]
@@ -190,13 +208,11 @@ class ViewSynthesisLossMixin:
     def _feature_metric(self, inputs, outputs, tgt_f, src_fs: Dict, coef: float, materialize=None):
         opt = self.opt
         frames = self._src_frames()
-        Kh, invKh = half_res_intrinsics(inputs["K"], inputs.get("inv_K"))
-        P = self._stack_P(inputs, outputs, Kh)
+        _, P, _, invKh3 = self._camera(inputs, outputs)
         cfg = FeatConfig(n_src=len(frames), min_depth=float(opt.min_depth), max_depth=float(opt.max_depth),
                          align_corners=self.grid_sample_align_corners, coef=float(coef),
                          materialize=self.materialize_outputs if materialize is None else materialize)
-        res = FeatureMetricLoss.apply(cfg, tgt_f, outputs[("disp", 0, 0)], P, invKh[:, :3, :3].contiguous(),
-                                      *[src_fs[f] for f in frames])
+        res = FeatureMetricLoss.apply(cfg, tgt_f, outputs[("disp", 0, 0)], P, invKh3, *[src_fs[f] for f in frames])
         if cfg.materialize:
             for i, f in enumerate(frames):
                 outputs[("feature", f, 0)] = res[1 + i]
@@ -245,6 +261,7 @@ class ViewSynthesisLossMixin:
         # independent until the losses are summed: issue them on two streams so that they share the SMs.  Autograd
         # runs each backward on its forward's stream, so the backward kernels overlap the same way.
         side = self._side_stream(tgt_f.device) if self.overlap_streams else None
+        self._camera(inputs, outputs)          # on the CURRENT stream, before the fork: both streams read its outputs
         if side is not None:
             main = torch.cuda.current_stream(tgt_f.device)
             side.wait_stream(main)

@@ -13,7 +13,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import EdgeArgs, EdgeMultiArgs, FeatArgs, PhotoArgs, PoseArgs, ReconArgs, TDL_MAX_LEVELS, TDL_MAX_SCALES, TDL_MAX_SRC
+from ._lib import EdgeArgs, EdgeMultiArgs, FeatArgs, PhotoArgs, PoseArgs, ProjArgs, ReconArgs, TDL_MAX_LEVELS, TDL_MAX_SCALES, TDL_MAX_SRC
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -503,3 +503,66 @@ class PoseTransform(torch.autograd.Function):
 def pose_transform(axisangle, translation, invert=False):
     """Drop-in for the reference's ``self.transformation_from_parameters(axisangle, translation, invert)`` on CUDA tensors."""
     return PoseTransform.apply(axisangle, translation, invert)
+
+
+# --------------------------------------------------------------------------------------------------
+class ProjectionPrologue(torch.autograd.Function):
+    """Everything the loss kernels need from the camera matrices in one launch each way (include/tdl.h tdl_proj_args):
+    forward(K (B,4,4), inv_K (B,4,4), *T (B,4,4) per source frame) -> (P_full (B,S,3,4), P_half (B,S,3,4),
+    invK3 (B,3,3), invKh3 (B,3,3)); gradients flow to the T's only (K, inv_K are data)."""
+
+    @staticmethod
+    def forward(ctx, K, inv_K, *Ts):
+        L = _lib.lib()
+        K, inv_K = _f32c(K, "K"), _f32c(inv_K, "inv_K")
+        Ts = [_f32c(t, "cam_T_cam") for t in Ts]
+        S, B = len(Ts), K.shape[0]
+        if not 1 <= S <= TDL_MAX_SRC or K.shape != (B, 4, 4) or inv_K.shape != (B, 4, 4) or any(t.shape != (B, 4, 4) for t in Ts):
+            raise _lib.TdlError("ProjectionPrologue: expected K, inv_K and 1..4 transforms of shape (B,4,4)")
+        dev = K.device
+        P_full = torch.empty((B, S, 3, 4), dtype=torch.float32, device=dev)
+        P_half = torch.empty_like(P_full)
+        invK3 = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+        invKh3 = torch.empty_like(invK3)
+        a = ProjArgs()
+        a.B, a.S = B, S
+        a.K, a.inv_K = K.data_ptr(), inv_K.data_ptr()
+        for f, t in enumerate(Ts):
+            a.T[f] = t.data_ptr()
+        a.P_full, a.P_half, a.invK3, a.invKh3 = P_full.data_ptr(), P_half.data_ptr(), invK3.data_ptr(), invKh3.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(L.tdl_proj_fwd(C.byref(a), _stream()), "tdl_proj_fwd")
+        ctx.S = S
+        ctx.save_for_backward(K)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(invK3, invKh3)
+        return P_full, P_half, invK3, invKh3
+
+    @staticmethod
+    def backward(ctx, g_full, g_half, *_unused):
+        L = _lib.lib()
+        (K,) = ctx.saved_tensors
+        S, B = ctx.S, K.shape[0]
+        need = ctx.needs_input_grad[2:2 + S]
+        if (g_full is None and g_half is None) or not any(need):
+            return (None, None, *([None] * S))
+        a = ProjArgs()
+        a.B, a.S = B, S
+        a.K = K.data_ptr()
+        if g_full is not None:
+            g_full = _f32c(g_full, "grad")
+            a.dP_full = g_full.data_ptr()
+        if g_half is not None:
+            g_half = _f32c(g_half, "grad")
+            a.dP_half = g_half.data_ptr()
+        dTs = [torch.empty((B, 4, 4), dtype=torch.float32, device=K.device) if need[f] else None for f in range(S)]
+        for f, t in enumerate(dTs):
+            if t is not None:
+                a.dT[f] = t.data_ptr()
+        with torch.cuda.device(K.device):
+            _lib.check(L.tdl_proj_bwd(C.byref(a), _stream()), "tdl_proj_bwd")
+        return (None, None, *dTs)
+
+
+def projection_prologue(K, inv_K, Ts):
+    return ProjectionPrologue.apply(K, inv_K, *Ts)
