@@ -19,10 +19,10 @@ namespace {
 
 // ---- process-wide tuning / test switches.  Read from the environment ONCE (first use) and afterwards only changed through
 // tdl_set_option(): the entry points below are on the training step's host path and must not call getenv().
-enum Opt { kOptNoTma = 0, kOptFusedFwd, kOptSparseMax, kOptFeatAtomic, kOptFeatChunk, kOptPhotoV1, kOptCount };
-const char* const kOptNames[kOptCount] = {"no_tma", "fused_fwd", "photo_sparse_max", "feat_atomic", "feat_chunk", "photo_v1"};
-const char* const kOptEnv[kOptCount] = {"TDL_NO_TMA", "TDL_FUSED_FWD", "TDL_PHOTO_SPARSE_MAX", "TDL_FEAT_ATOMIC", "TDL_FEAT_CHUNK", "TDL_PHOTO_V1"};
-const int kOptDefault[kOptCount] = {0, 0, 128, 0, 0, 0};
+enum Opt { kOptNoTma = 0, kOptFusedFwd, kOptSparseMax, kOptFeatAtomic, kOptFeatChunk, kOptPhotoV1, kOptListMax, kOptCount };
+const char* const kOptNames[kOptCount] = {"no_tma", "fused_fwd", "photo_sparse_max", "feat_atomic", "feat_chunk", "photo_v1", "photo_list_max"};
+const char* const kOptEnv[kOptCount] = {"TDL_NO_TMA", "TDL_FUSED_FWD", "TDL_PHOTO_SPARSE_MAX", "TDL_FEAT_ATOMIC", "TDL_FEAT_CHUNK", "TDL_PHOTO_V1", "TDL_PHOTO_LIST_MAX"};
+const int kOptDefault[kOptCount] = {0, 0, 128, 0, 0, 0, kListCap};
 std::atomic<int> g_opt[kOptCount];
 std::once_flag g_opt_once;
 
@@ -30,7 +30,7 @@ void init_options() {
     for (int i = 0; i < kOptCount; ++i) {
         const char* e = getenv(kOptEnv[i]);
         int v = kOptDefault[i];
-        if (e) v = (i == kOptSparseMax || i == kOptFeatChunk) ? atoi(e) : 1;
+        if (e) v = (i == kOptSparseMax || i == kOptFeatChunk || i == kOptListMax) ? atoi(e) : 1;
         g_opt[i].store(v, std::memory_order_relaxed);
     }
 }
@@ -70,14 +70,16 @@ inline bool pow2_factor(int big, int small, int* fac) {
 }
 
 struct PhotoWsLayout {
-    uint64_t acc_off, j_off[TDL_MAX_SCALES], w_off[TDL_MAX_SCALES], argmin_off, total;
+    uint64_t acc_off, acc_doubles, j_off[TDL_MAX_SCALES], w_off[TDL_MAX_SCALES], argmin_off, list_off, total;
 };
 
 PhotoWsLayout photo_layout(int B, int H, int W, int nscales, const int32_t* dh, const int32_t* dw) {
     PhotoWsLayout L;
     uint64_t off = 0;
     L.acc_off = off;
-    off = align_up(off + (uint64_t)nscales * B * 4 * sizeof(double), 256);
+    // per-image sums, then the work-list header (int count per (scale, image) + the validity word), cleared together
+    L.acc_doubles = (uint64_t)nscales * B * 4 + ((uint64_t)nscales * B + 1 + 1) / 2;
+    off = align_up(off + L.acc_doubles * sizeof(double), 256);
     for (int s = 0; s < TDL_MAX_SCALES; ++s) {
         L.j_off[s] = off;
         if (s < nscales) off = align_up(off + (uint64_t)B * 3 * dh[s] * dw[s] * sizeof(float), 256);
@@ -86,6 +88,8 @@ PhotoWsLayout photo_layout(int B, int H, int W, int nscales, const int32_t* dh, 
     }
     L.argmin_off = off;
     off = align_up(off + (uint64_t)nscales * B * H * W, 256);
+    L.list_off = off;
+    off = align_up(off + (uint64_t)nscales * B * kListCap * sizeof(uint32_t), 256);
     L.total = off;
     return L;
 }
@@ -131,6 +135,9 @@ int check_photo(const tdl_photo_args* a, bool bwd, PhotoDev* d) {
         d->Wt[s] = reinterpret_cast<float*>(ws + L.w_off[s]);
     }
     d->argmin = reinterpret_cast<unsigned char*>(ws + L.argmin_off);
+    d->acc_n = (int)L.acc_doubles;
+    d->lcnt = reinterpret_cast<int*>(d->acc + (size_t)a->nscales * a->B * 4);
+    d->wlist = reinterpret_cast<uint32_t*>(ws + L.list_off);
     d->automask = a->automask != 0;
     d->use_tma = !opt(kOptNoTma);
     d->split_fwd = !opt(kOptFusedFwd);
@@ -140,6 +147,13 @@ int check_photo(const tdl_photo_args* a, bool bwd, PhotoDev* d) {
         // limit (9 live pixels per window must fit the tile's list).  Tests: 0 forces the dense backward everywhere.
         const int v = opt(kOptSparseMax);
         d->sparse_max = v < 0 ? 0 : (v > 128 ? 128 : v);
+    }
+    {
+        // (image, scale) pairs with <= list_max selected windows (default: the list capacity, 3 % of a 192x640 image) are
+        // differentiated from the work list; -1 switches the list path off (tests).  The entries carry the pixel in 28 bits.
+        const int v = opt(kOptListMax);
+        d->list_max = v < -1 ? -1 : (v > kListCap ? kListCap : v);
+        if ((uint64_t)a->H * a->W >= (1ull << 28)) d->list_max = -1;
     }
     d->align_corners = a->align_corners != 0;
     d->min_disp = (float)(1.0 / a->max_depth);
@@ -267,7 +281,7 @@ int tdl_get_option(const char* name, int* value) {
 int tdl_launch_count(const char* entry) {
     if (!entry) return 0;
     if (!strcmp(entry, "tdl_photo_fwd")) return 4;        // photo_warp + photo_score (or fused photo_fwd), smooth_fwd, finalize
-    if (!strcmp(entry, "tdl_photo_bwd")) return 2;        // smooth_bwd, photo_bwd
+    if (!strcmp(entry, "tdl_photo_bwd")) return opt(kOptListMax) >= 0 ? 3 : 2;   // smooth_bwd, photo_bwd, photo_bwd_list
     if (!strcmp(entry, "tdl_feat_fwd")) return 2;         // feat_fwd, finalize
     if (!strcmp(entry, "tdl_feat_bwd")) return 1;         // feat_bwd (atomic scatter / frozen features)
     if (!strcmp(entry, "tdl_feat_bwd:gather")) return 3;  // feat_bwd (bucket) + feat_gather + feat_overflow (bwd_scratch given)
@@ -334,7 +348,7 @@ int tdl_photo_fwd(const tdl_photo_args* a, tdl_stream_t stream) {
         TDL_KERNEL("photo_warp", launch_photo_warp(d, st));
         TDL_KERNEL("photo_score", d.v1 ? launch_photo_score(d, st) : launch_photo_score2(d, st));
     } else {
-        TDL_KERNEL("memset", cudaMemsetAsync(d.acc, 0, (size_t)a->nscales * a->B * 4 * sizeof(double), st));
+        TDL_KERNEL("memset", cudaMemsetAsync(d.acc, 0, (size_t)d.acc_n * sizeof(double), st));
         TDL_KERNEL("photo_fwd", launch_photo_fwd(d, st));
     }
     SmoothDev sm;
@@ -356,6 +370,7 @@ int tdl_photo_bwd(const tdl_photo_args* a, tdl_stream_t stream) {
     sm.zero_n = a->B * a->S * 12;
     TDL_KERNEL("smooth_bwd", launch_smooth_bwd(sm, st));       // writes d_disp[s] (=), the photometric kernel adds to it
     TDL_KERNEL("photo_bwd", launch_photo_bwd(d, st));
+    if (d.list_max >= 0 && photo_fwd_can_split(d)) TDL_KERNEL("photo_bwd_list", launch_photo_bwd_list(d, st));
     return TDL_OK;
 }
 

@@ -32,6 +32,9 @@ struct DepthParamsH {
 };
 
 // ---- photometric + smoothness, device-side view of tdl_photo_args -------------
+constexpr int kListCap = 4096;           // work-list entries per (image, scale)
+constexpr int kListMagic = 0x5C0DE2;     // written by photo_score2_kernel after the lists of a forward are complete
+
 struct PhotoDev {
     int B, H, W, S, nscales;
     int dh[TDL_MAX_SCALES], dw[TDL_MAX_SCALES], fac[TDL_MAX_SCALES];
@@ -42,6 +45,8 @@ struct PhotoDev {
     int v1;                      // use the round-1 scoring kernel (A/B comparisons and tests)
     int sparse_max;              // backward: tiles with at most this many selected windows (of 1156 incl. halo) scatter
                                  // their adjoint instead of running the dense box-sum gather (auto-masked regions)
+    int list_max;                // backward: (image, scale) pairs with at most this many selected windows run from the work list
+                                 // the scoring kernel emitted (static scenes: auto-masking leaves ~1 % of the windows); -1: off
     float min_disp, range;
     uint64_t seed;
     const float* target;
@@ -54,6 +59,9 @@ struct PhotoDev {
     long long* min_index[TDL_MAX_SCALES];
     // workspace
     double* acc;                 // [nscales][B][4]: photo sum, disp sum, smooth first, smooth second
+    int acc_n;                   // doubles cleared at the start of every forward: the sums above + the work-list header
+    int* lcnt;                   // [nscales*B] selected windows per (scale, image) | [nscales*B] = kListMagic once the lists are valid
+    uint32_t* wlist;             // [nscales*B][kListCap] selected windows: pixel | frame << 28
     unsigned char* argmin;       // [nscales][B][H][W]
     float* J[TDL_MAX_SCALES];    // area-downsampled target (B,3,dh,dw)
     float* Wt[TDL_MAX_SCALES];   // smoothness edge weights (B,6,dh,dw)
@@ -145,6 +153,7 @@ cudaError_t launch_photo_warp(const PhotoDev& p, cudaStream_t st);
 cudaError_t launch_photo_score(const PhotoDev& p, cudaStream_t st);      // round-1 strip kernel (option photo_v1)
 cudaError_t launch_photo_score2(const PhotoDev& p, cudaStream_t st);     // register micro-tile kernel (tdl_photo2.cu)
 cudaError_t launch_photo_bwd(const PhotoDev& p, cudaStream_t st);
+cudaError_t launch_photo_bwd_list(const PhotoDev& p, cudaStream_t st);   // work-list backward of sparsely selected images
 cudaError_t launch_smooth_fwd(const SmoothDev& p, cudaStream_t st);
 cudaError_t launch_smooth_bwd(const SmoothDev& p, cudaStream_t st);
 cudaError_t launch_area_pyramid(const float* img, int B, int H, int W, float* J, int h, int w, cudaStream_t st);

@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256, 1) photo_warp_kernel(const PhotoDev p) {
     __syncthreads();
     // the scoring / smoothness kernels that follow accumulate their per-image sums into p.acc: cleared here (one launch less)
     if (blockIdx.x == 0 && b == 0)
-        for (int i = tid; i < p.nscales * p.B * 4; i += 256) p.acc[i] = 0.0;
+        for (int i = tid; i < p.acc_n; i += 256) p.acc[i] = 0.0;          // (+ the work-list header)
     const int pix = blockIdx.x * 256 + tid;
     if (pix >= (int)HW) return;
     const int y = pix / W, x = pix - y * W;
@@ -660,6 +660,24 @@ __global__ void __launch_bounds__(kNT, 2) photo_score_kernel(const PhotoDev p, c
 // factor of the mean over the window, kept from round 1): with the scaled sums Sx = 9 mu_x ... the chain rule gives
 //     d v / d x_q = [ q Sx (d2 - d1) - Sy (n2 - n1) ] / d  +  x_q * 9 q d1 / d  +  y_q * (-9 n1 / d),      q = n / d,
 // so cA = 9k (...)/d, 2 cB = 9k * 9 q d1 / d, cC = -9k * 9 n1 / d.
+TDL_DEV void window_coefs(float sx, float sy, float sxx, float syy, float sxy, float k, float& cA, float& cB, float& cC) {
+    const float n1 = fmaf(sx, sy, fmaf(sx, sy, kK1));
+    const float d1 = fmaf(sx, sx, fmaf(sy, sy, kK1));
+    const float n2 = fmaf(-sx, sy, fmaf(9.f, sxy, fmaf(9.f, sxy, fmaf(-sx, sy, kK2))));
+    const float d2 = fmaf(-sx, sx, fmaf(9.f, sxx, fmaf(9.f, syy, fmaf(-sy, sy, kK2))));
+    const float n = __fmul_rn(n1, n2), d = __fmul_rn(d1, d2);
+    const float e = __fsub_rn(d, n);                           // v = e / (2 d): the clamp passes gradient for 0 <= v <= 1
+    cA = cB = cC = 0.f;
+    if (e >= 0.f && e <= 2.f * d) {
+        const float rd = rcp_newton(d);
+        const float q = n * rd;
+        const float k9 = 9.f * k * rd;
+        cA = k9 * fmaf(q * sx, d2 - d1, -sy * (n2 - n1));
+        cB = 4.5f * k9 * q * d1;
+        cC = -9.f * k9 * n1;
+    }
+}
+
 template <int PITCH>
 TDL_DEV void window_adjoint(const float* __restrict__ xs, const float* __restrict__ ys, float k, float& cA, float& cB,
                             float& cC) {
@@ -676,21 +694,7 @@ TDL_DEV void window_adjoint(const float* __restrict__ xs, const float* __restric
             sxy = fmaf(xv, yv, sxy);
         }
     }
-    const float n1 = fmaf(sx, sy, fmaf(sx, sy, kK1));
-    const float d1 = fmaf(sx, sx, fmaf(sy, sy, kK1));
-    const float n2 = fmaf(-sx, sy, fmaf(9.f, sxy, fmaf(9.f, sxy, fmaf(-sx, sy, kK2))));
-    const float d2 = fmaf(-sx, sx, fmaf(9.f, sxx, fmaf(9.f, syy, fmaf(-sy, sy, kK2))));
-    const float n = __fmul_rn(n1, n2), d = __fmul_rn(d1, d2);
-    const float e = __fsub_rn(d, n);                           // v = e / (2 d): the clamp passes gradient for 0 <= v <= 1
-    cA = cB = cC = 0.f;
-    if (e >= 0.f && e <= 2.f * d) {
-        const float rd = rcp_newton(d);
-        const float q = n * rd;
-        const float k9 = 9.f * k * rd;
-        cA = k9 * fmaf(q * sx, d2 - d1, -sy * (n2 - n1));
-        cB = 4.5f * k9 * q * d1;
-        cC = -9.f * k9 * n1;
-    }
+    window_coefs(sx, sy, sxx, syy, sxy, k, cA, cB, cC);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -732,6 +736,9 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     // Everything the CTA needs from global memory is requested up front -- the TMA box copies, the arg-min bytes and
     // the disparity taps below do not depend on shared memory -- so one memory latency sits on the critical path instead
     // of three (cam/tables -> barrier -> gathers -> barrier -> tiles): 280 -> 2xx us on the bench shape.
+    // (image, scale) pairs whose selected windows fit the work list the scoring kernel emitted are differentiated by
+    // photo_bwd_list_kernel: their tiles leave before anything is requested (static scenes: ~1 % of the windows selected)
+    if (p.list_max >= 0 && p.lcnt[p.nscales * p.B] == kListMagic && p.lcnt[s * p.B + b] <= p.list_max) return;   // CTA-uniform
     if (kTMA && tid == 0) {
         // one elected thread stages the target and the S warped tiles (halo 2) with 3-D TMA box copies
         mbar_init(&s_bar, 1);
@@ -1265,6 +1272,159 @@ cudaError_t launch_photo_score(const PhotoDev& p, cudaStream_t st) {
     return cudaErrorInvalidValue;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Work-list backward.  For an (image, scale) pair in which auto-masking left only a few windows selected (a static scene:
+// ~1 % of the pixels), staging every tile to find a dozen windows each is what costs -- photo_bwd_kernel spent 110-130 us
+// on a batch of such images.  photo_score2_kernel appends every selected window (pixel | frame << 28) to a per-(scale,
+// image) list while it writes the arg-min; here ONE THREAD per (list entry, tap of its 3x3 window) works straight from
+// global memory: it forms the window sums of the three channels itself (the nine threads of a window read the same 54
+// values: one L1 line each), takes its tap's d loss / d warped value, and runs the sampling and projection adjoint of
+// that pixel -- the chain is linear in the incoming gradient, so the contributions of overlapping windows need not be
+// combined first.  Taps outside the image are their mirror pixel (nn.ReflectionPad2d(1)).  4 atomics per thread into
+// d_disp_s; the pose adjoint leaves through a warp reduction per frame + shared-memory atomics + one global atomic per CTA.
+// The kernel is a chain of three dependent memory latencies with a few hundred instructions in between, so what matters
+// is threads in flight: 9 per window, no shared memory, <= 64 registers.
+// Pairs with more than list_max windows are left to photo_bwd_kernel, which in turn skips the listed ones.
+constexpr int kListCtas = 72;            // CTAs per (scale, image): 72 x 256 threads = 2048 windows per sweep
+
+template <int S>
+__global__ void __launch_bounds__(256, 4) photo_bwd_list_kernel(const PhotoDev p) {
+    __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
+    __shared__ float s_dP[TDL_MAX_SRC * 12];
+    const int tid = threadIdx.x;
+    const int bs = blockIdx.y, s = bs / p.B, b = bs - s * p.B;
+    const int n = p.lcnt[bs];
+    if (p.lcnt[p.nscales * p.B] != kListMagic || n > p.list_max || (int)(blockIdx.x * 256) >= 9 * n) return;   // CTA-uniform
+    const int H = p.H, W = p.W, h = p.dh[s], w = p.dw[s];
+    const size_t HW = (size_t)H * W;
+    const ProjConst pcst = make_proj_const(H, W, p.align_corners);
+    if (tid < S * 12) {
+        s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
+        s_dP[tid] = 0.f;
+    }
+    if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
+    __syncthreads();
+    const float* s_iK = s_cam + TDL_MAX_SRC * 12;
+    const DepthParams dp{p.min_disp, p.range};
+    const float up = __ldg(p.dlosses + s) * p.photo_coef[s] / ((float)p.B * (float)H * (float)W);
+    const float g_ssim = up * 0.85f / 3.f, g_l1 = up * 0.15f / 3.f;
+    const float* db = p.disp[s] + (size_t)b * h * w;
+    float* dd = p.d_disp[s] + (size_t)b * h * w;
+    const uint32_t* wl = p.wlist + (size_t)bs * kListCap;
+    const float* tb = p.target + (size_t)b * 3 * HW;
+
+    for (int i0 = blockIdx.x * 256; i0 < 9 * n; i0 += gridDim.x * 256) {                   // CTA-uniform trip count
+        const int idx = i0 + tid;
+        const bool on = idx < 9 * n;
+        const int e = on ? idx / 9 : 0, tap = on ? idx - 9 * e : 0;
+        const uint32_t ent = __ldg(wl + e);
+        const int f = (int)(ent >> 28), pix = (int)(ent & 0x0fffffffu);
+        const int wy = pix / W, wx = pix - wy * W;
+        const float* wbase = p.warped[s][0];
+        const float* sbase = p.src[0];
+#pragma unroll
+        for (int k = 1; k < S; ++k)
+            if (k == f) {
+                wbase = p.warped[s][k];
+                sbase = p.src[k];
+            }
+        wbase += (size_t)b * 3 * HW;
+        sbase += (size_t)b * 3 * HW;
+        // the window: rows / columns reflected once, then 9 taps x 3 channels x (warped, target)
+        int ry[3], rx[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            ry[k] = reflect1(wy + k - 1, H) * W;
+            rx[k] = reflect1(wx + k - 1, W);
+        }
+        const int ty = tap / 3, tx = tap - 3 * ty;
+        const int py = reflect1(wy + ty - 1, H), px = reflect1(wx + tx - 1, W);             // this thread's pixel
+        // (the disparity taps of this thread's pixel do not depend on the window values: requested first)
+        const UpTap ut = up_tap(py, px, p.sy[s], p.sx[s], h, w);
+        const float dv = up_value(db, w, ut);
+        float G[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f, xt = 0.f, yt = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {                                                   // tap order of window_adjoint
+                const int o = ry[k / 3] + rx[k % 3];
+                const float xv = __ldg(wbase + ch * HW + o), yv = __ldg(tb + ch * HW + o);
+                sx += xv;
+                sy += yv;
+                sxx = fmaf(xv, xv, sxx);
+                syy = fmaf(yv, yv, syy);
+                sxy = fmaf(xv, yv, sxy);
+                if (k == tap) {
+                    xt = xv;
+                    yt = yv;
+                }
+            }
+            float cA, cB, cC;
+            window_coefs(sx, sy, sxx, syy, sxy, g_ssim * (1.f / 9.f), cA, cB, cC);
+            G[ch] = cA + 2.f * xt * cB + yt * cC;
+            if (tap == 4) {                                                                 // robust-L1 term of the centre
+                const float df = xt - yt;
+                G[ch] += g_l1 * df * rsqrt_approx(df * df + kL1Eps2);
+            }
+        }
+        const float* Pf = s_cam + f * 12;
+        const Geo g = backproject(dv, dp, s_iK, px, py);
+        const Proj pr = project<true>(g, Pf, pcst);
+        const Bilin bt = bilin_taps(pr.ix, pr.iy, H, W);
+        const float* q = sbase + (size_t)bt.y0 * W + bt.x0;
+        const int dx = bt.vx ? 1 : 0, dy = bt.vy ? W : 0;
+        float gix = 0.f, giy = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float v00 = __ldg(q + ch * HW), v01 = bt.vx ? __ldg(q + ch * HW + dx) : 0.f;
+            const float v10 = bt.vy ? __ldg(q + ch * HW + dy) : 0.f;
+            const float v11 = (bt.vx && bt.vy) ? __ldg(q + ch * HW + dy + dx) : 0.f;
+            const float dix = -v00 * bt.ey + v01 * bt.ey - v10 * bt.ay + v11 * bt.ay;
+            const float diy = -v00 * bt.ex - v01 * bt.ax + v10 * bt.ex + v11 * bt.ax;
+            gix += G[ch] * dix;
+            giy += G[ch] * diy;
+        }
+        const float gu = gix * pr.mx, gv = giy * pr.my;
+        const float rz = rcp_newton(pr.z);
+        const float gp0 = on ? gu * rz : 0.f, gp1 = on ? gv * rz : 0.f, gp2 = on ? -(gu * pr.u + gv * pr.v) * rz : 0.f;
+        float aP[12];
+        aP[0] = gp0 * g.X0; aP[1] = gp0 * g.X1; aP[2] = gp0 * g.X2; aP[3] = gp0;
+        aP[4] = gp1 * g.X0; aP[5] = gp1 * g.X1; aP[6] = gp1 * g.X2; aP[7] = gp1;
+        aP[8] = gp2 * g.X0; aP[9] = gp2 * g.X1; aP[10] = gp2 * g.X2; aP[11] = gp2;
+#pragma unroll 1
+        for (int ff = 0; ff < S; ++ff) {                      // 12-value warp reduction per frame, one shared atomic per value
+            float a2[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) a2[k] = (f == ff) ? aP[k] : 0.f;
+            float tot;
+            const int slot = warp_sum12(a2, tot);
+            if (slot >= 0 && tot != 0.f) atomicAdd(&s_dP[ff * 12 + slot], tot);
+        }
+        if (gp0 != 0.f || gp1 != 0.f || gp2 != 0.f) {
+            const float gX0 = Pf[0] * gp0 + Pf[4] * gp1 + Pf[8] * gp2;
+            const float gX1 = Pf[1] * gp0 + Pf[5] * gp1 + Pf[9] * gp2;
+            const float gX2 = Pf[2] * gp0 + Pf[6] * gp1 + Pf[10] * gp2;
+            const float gD = gX0 * g.r0 + gX1 * g.r1 + gX2 * g.r2;
+            const float gdisp = -p.range * g.D * g.D * gD;
+            const float hy = 1.f - ut.ly, hx = 1.f - ut.lx;           // adjoint of the bilinear up-sampling, straight to d_disp_s
+            atomicAdd(dd + (size_t)ut.y0 * w + ut.x0, hy * hx * gdisp);
+            atomicAdd(dd + (size_t)ut.y0 * w + ut.x1, hy * ut.lx * gdisp);
+            atomicAdd(dd + (size_t)ut.y1 * w + ut.x0, ut.ly * hx * gdisp);
+            atomicAdd(dd + (size_t)ut.y1 * w + ut.x1, ut.ly * ut.lx * gdisp);
+        }
+    }
+    __syncthreads();
+    if (tid < S * 12 && s_dP[tid] != 0.f) atomicAdd(p.dP + ((size_t)b * S) * 12 + tid, s_dP[tid]);
+}
+
+template <int S>
+static cudaError_t launch_bwd_list_t(const PhotoDev& p, cudaStream_t st) {
+    dim3 grid(kListCtas, p.nscales * p.B);
+    photo_bwd_list_kernel<S><<<grid, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
 template <int S, bool kTMA>
 static cudaError_t launch_bwd_k(const PhotoDev& p, const PhotoMaps& maps, cudaStream_t st) {
     const size_t smem = (size_t)((1 + S) * kQGROUP + 9 * kQPLANE) * sizeof(float) + kQPLANE;
@@ -1298,6 +1458,11 @@ cudaError_t launch_photo_bwd(const PhotoDev& p, cudaStream_t st) {
         case 3: return launch_bwd_t<3>(p, st);
         case 4: return launch_bwd_t<4>(p, st);
     }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_photo_bwd_list(const PhotoDev& p, cudaStream_t st) {
+    TDL_DISPATCH_S(launch_bwd_list_t, p, st)
     return cudaErrorInvalidValue;
 }
 

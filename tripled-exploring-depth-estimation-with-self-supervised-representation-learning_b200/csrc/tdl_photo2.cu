@@ -310,10 +310,10 @@ __global__ void __launch_bounds__(s2::NT, S <= 2 ? 3 : 2) photo_score2_kernel(co
         __syncthreads();
 
         // ---- reprojection errors of the warped frames, minimum over all channels
+        const int chan0 = p.automask ? S : 0;
         {
             float rho[S][kPP];
             score_frames(s_img, rho);
-            const int chan0 = p.automask ? S : 0;
 #pragma unroll
             for (int f = 0; f < S; ++f)
 #pragma unroll
@@ -340,8 +340,38 @@ __global__ void __launch_bounds__(s2::NT, S <= 2 ? 3 : 2) photo_score2_kernel(co
 #pragma unroll
         for (int q = 0; q < TDL_MAX_SCALES; ++q)
             if (q == s) lsum[q] = ls;
+        // ---- work list of the backward (photo_bwd_list_kernel): every window whose arg-min is a warped frame is appended
+        //      to the list of its (scale, image) as pixel | frame << 28; one atomic per warp reserves the slots.  The count
+        //      keeps running past the capacity (the backward then knows the list is incomplete and runs the tile kernel).
+        if (p.list_max >= 0) {
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < kPP; ++i) cnt += (arg[i] >= chan0 && gy0 + i / kPC < H && gx0 < W) ? 1 : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            int base = 0;
+            if (lane == 31 && incl > 0) base = atomicAdd(p.lcnt + s * p.B + b, incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            if (cnt > 0 && base < kListCap) {
+                int off = base + incl - cnt;
+                uint32_t* wl = p.wlist + ((size_t)s * p.B + b) * kListCap;
+#pragma unroll
+                for (int i = 0; i < kPP; ++i) {
+                    const int gy = gy0 + i / kPC, gx = gx0 + i % kPC;
+                    if (arg[i] >= chan0 && gy < H && gx0 < W) {
+                        if (off < kListCap) wl[off] = (uint32_t)(gy * W + gx) | ((uint32_t)(arg[i] - chan0) << 28);
+                        ++off;
+                    }
+                }
+            }
+        }
         __syncthreads();           // every thread is done with this scale's tiles before the next TMA overwrites them
     }
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.lcnt[p.nscales * p.B] = kListMagic;
     // ---- one CTA reduction for the 2 * nscales partial sums
 #pragma unroll
     for (int q = 0; q < TDL_MAX_SCALES; ++q) {
