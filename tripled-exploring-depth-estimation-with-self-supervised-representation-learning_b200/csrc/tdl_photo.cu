@@ -1276,25 +1276,28 @@ cudaError_t launch_photo_score(const PhotoDev& p, cudaStream_t st) {
 // Work-list backward.  For an (image, scale) pair in which auto-masking left only a few windows selected (a static scene:
 // ~1 % of the pixels), staging every tile to find a dozen windows each is what costs -- photo_bwd_kernel spent 110-130 us
 // on a batch of such images.  photo_score2_kernel appends every selected window (pixel | frame << 28) to a per-(scale,
-// image) list while it writes the arg-min; here ONE THREAD per (list entry, tap of its 3x3 window) works straight from
-// global memory: it forms the window sums of the three channels itself (the nine threads of a window read the same 54
-// values: one L1 line each), takes its tap's d loss / d warped value, and runs the sampling and projection adjoint of
-// that pixel -- the chain is linear in the incoming gradient, so the contributions of overlapping windows need not be
-// combined first.  Taps outside the image are their mirror pixel (nn.ReflectionPad2d(1)).  4 atomics per thread into
-// d_disp_s; the pose adjoint leaves through a warp reduction per frame + shared-memory atomics + one global atomic per CTA.
-// The kernel is a chain of three dependent memory latencies with a few hundred instructions in between, so what matters
-// is threads in flight: 9 per window, no shared memory, <= 64 registers.
+// image) list while it writes the arg-min; here NINE THREADS per list entry work straight from global memory.  Read as
+// (channel, window row) each loads 3 taps of the warped and the target image into shared memory (27 x 2 values per
+// window, once); one thread per channel forms the window sums and the SSIM adjoint coefficients; read as TAP each thread then
+// takes d loss / d warped value of its pixel and runs the sampling and projection adjoint for it -- the chain is linear
+// in the incoming gradient, so the contributions of overlapping windows need not be combined first.  Taps outside the
+// image are their mirror pixel (nn.ReflectionPad2d(1)).  4 atomics per thread into d_disp_s; the pose adjoint leaves
+// through a warp reduction per frame + shared-memory atomics + one global atomic per CTA.  The kernel is a chain of three
+// dependent memory latencies with ~800 instructions in between, so what matters is threads in flight (<= 64 registers).
 // Pairs with more than list_max windows are left to photo_bwd_kernel, which in turn skips the listed ones.
-constexpr int kListCtas = 72;            // CTAs per (scale, image): 72 x 256 threads = 2048 windows per sweep
+constexpr int kListWin = 28;             // windows per CTA sweep: 9 threads each (252 of 256 threads)
+constexpr int kListCtas = 74;            // CTAs per (scale, image): 2072 windows per sweep of the grid
 
 template <int S>
 __global__ void __launch_bounds__(256, 4) photo_bwd_list_kernel(const PhotoDev p) {
     __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
     __shared__ float s_dP[TDL_MAX_SRC * 12];
+    __shared__ float2 s_xy[kListWin][3][9];          // (warped, target) value of every tap of the CTA's windows
+    __shared__ float s_cf[kListWin][3][3];           // per channel: cA, cB, cC (window_coefs)
     const int tid = threadIdx.x;
     const int bs = blockIdx.y, s = bs / p.B, b = bs - s * p.B;
     const int n = p.lcnt[bs];
-    if (p.lcnt[p.nscales * p.B] != kListMagic || n > p.list_max || (int)(blockIdx.x * 256) >= 9 * n) return;   // CTA-uniform
+    if (p.lcnt[p.nscales * p.B] != kListMagic || n > p.list_max || (int)(blockIdx.x * kListWin) >= n) return;   // CTA-uniform
     const int H = p.H, W = p.W, h = p.dh[s], w = p.dw[s];
     const size_t HW = (size_t)H * W;
     const ProjConst pcst = make_proj_const(H, W, p.align_corners);
@@ -1303,7 +1306,6 @@ __global__ void __launch_bounds__(256, 4) photo_bwd_list_kernel(const PhotoDev p
         s_dP[tid] = 0.f;
     }
     if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
-    __syncthreads();
     const float* s_iK = s_cam + TDL_MAX_SRC * 12;
     const DepthParams dp{p.min_disp, p.range};
     const float up = __ldg(p.dlosses + s) * p.photo_coef[s] / ((float)p.B * (float)H * (float)W);
@@ -1312,12 +1314,14 @@ __global__ void __launch_bounds__(256, 4) photo_bwd_list_kernel(const PhotoDev p
     float* dd = p.d_disp[s] + (size_t)b * h * w;
     const uint32_t* wl = p.wlist + (size_t)bs * kListCap;
     const float* tb = p.target + (size_t)b * 3 * HW;
+    // thread = (window j of the sweep, r9): r9 is the TAP whose pixel the thread differentiates, and -- read as
+    // (channel, window row) -- the part of the window sums it contributes
+    const int j = tid / 9, r9 = tid - 9 * j;
+    const int ch_a = r9 / 3, row_a = r9 - 3 * ch_a;
 
-    for (int i0 = blockIdx.x * 256; i0 < 9 * n; i0 += gridDim.x * 256) {                   // CTA-uniform trip count
-        const int idx = i0 + tid;
-        const bool on = idx < 9 * n;
-        const int e = on ? idx / 9 : 0, tap = on ? idx - 9 * e : 0;
-        const uint32_t ent = __ldg(wl + e);
+    for (int e0 = blockIdx.x * kListWin; e0 < n; e0 += gridDim.x * kListWin) {             // CTA-uniform trip count
+        const bool on = j < kListWin && e0 + j < n;
+        const uint32_t ent = on ? __ldg(wl + e0 + j) : 0u;
         const int f = (int)(ent >> 28), pix = (int)(ent & 0x0fffffffu);
         const int wy = pix / W, wx = pix - wy * W;
         const float* wbase = p.warped[s][0];
@@ -1330,42 +1334,49 @@ __global__ void __launch_bounds__(256, 4) photo_bwd_list_kernel(const PhotoDev p
             }
         wbase += (size_t)b * 3 * HW;
         sbase += (size_t)b * 3 * HW;
-        // the window: rows / columns reflected once, then 9 taps x 3 channels x (warped, target)
-        int ry[3], rx[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            ry[k] = reflect1(wy + k - 1, H) * W;
-            rx[k] = reflect1(wx + k - 1, W);
-        }
-        const int ty = tap / 3, tx = tap - 3 * ty;
+        // taps outside the image are their mirror pixel (nn.ReflectionPad2d(1))
+        const int ty = r9 / 3, tx = r9 - 3 * ty;
         const int py = reflect1(wy + ty - 1, H), px = reflect1(wx + tx - 1, W);             // this thread's pixel
-        // (the disparity taps of this thread's pixel do not depend on the window values: requested first)
+        // (the disparity taps of the pixel do not depend on the window values: requested first)
         const UpTap ut = up_tap(py, px, p.sy[s], p.sx[s], h, w);
         const float dv = up_value(db, w, ut);
-        float G[3];
+        if (on) {                                                // one window row of one channel: 3 taps of warped + target
+            const size_t ro = (size_t)ch_a * HW + (size_t)reflect1(wy + row_a - 1, H) * W;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f, xt = 0.f, yt = 0.f;
+            for (int c = 0; c < 3; ++c) {
+                const int cx = reflect1(wx + c - 1, W);
+                s_xy[j][ch_a][row_a * 3 + c] = make_float2(__ldg(wbase + ro + cx), __ldg(tb + ro + cx));
+            }
+        }
+        __syncthreads();                                         // (also: s_cam / s_dP of the prologue)
+        if (on && r9 < 3) {                                      // one thread per (window, channel): the coefficients, with
+            float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;      // the sums in the tap order of window_adjoint
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {                                                   // tap order of window_adjoint
-                const int o = ry[k / 3] + rx[k % 3];
-                const float xv = __ldg(wbase + ch * HW + o), yv = __ldg(tb + ch * HW + o);
-                sx += xv;
-                sy += yv;
-                sxx = fmaf(xv, xv, sxx);
-                syy = fmaf(yv, yv, syy);
-                sxy = fmaf(xv, yv, sxy);
-                if (k == tap) {
-                    xt = xv;
-                    yt = yv;
-                }
+            for (int k = 0; k < 9; ++k) {
+                const float2 v = s_xy[j][r9][k];
+                sx += v.x;
+                sy += v.y;
+                sxx = fmaf(v.x, v.x, sxx);
+                syy = fmaf(v.y, v.y, syy);
+                sxy = fmaf(v.x, v.y, sxy);
             }
             float cA, cB, cC;
             window_coefs(sx, sy, sxx, syy, sxy, g_ssim * (1.f / 9.f), cA, cB, cC);
-            G[ch] = cA + 2.f * xt * cB + yt * cC;
-            if (tap == 4) {                                                                 // robust-L1 term of the centre
-                const float df = xt - yt;
-                G[ch] += g_l1 * df * rsqrt_approx(df * df + kL1Eps2);
+            s_cf[j][r9][0] = cA;
+            s_cf[j][r9][1] = cB;
+            s_cf[j][r9][2] = cC;
+        }
+        __syncthreads();
+        float G[3] = {0.f, 0.f, 0.f};
+        if (on) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float2 v = s_xy[j][ch][r9];
+                G[ch] = s_cf[j][ch][0] + 2.f * v.x * s_cf[j][ch][1] + v.y * s_cf[j][ch][2];
+                if (r9 == 4) {                                                              // robust-L1 term of the centre
+                    const float df = v.x - v.y;
+                    G[ch] += g_l1 * df * rsqrt_approx(df * df + kL1Eps2);
+                }
             }
         }
         const float* Pf = s_cam + f * 12;
@@ -1413,8 +1424,8 @@ __global__ void __launch_bounds__(256, 4) photo_bwd_list_kernel(const PhotoDev p
             atomicAdd(dd + (size_t)ut.y1 * w + ut.x0, ut.ly * hx * gdisp);
             atomicAdd(dd + (size_t)ut.y1 * w + ut.x1, ut.ly * ut.lx * gdisp);
         }
+        __syncthreads();                                         // the shared window tables are rewritten by the next sweep
     }
-    __syncthreads();
     if (tid < S * 12 && s_dP[tid] != 0.f) atomicAdd(p.dP + ((size_t)b * S) * 12 + tid, s_dP[tid]);
 }
 
