@@ -112,8 +112,11 @@ __global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) 
     auto slot = [&](int stage, int row) { return ring + ((size_t)(stage * kRowsPerStep + row) * 32 + lane) * kLaneBytes; };
     auto cp_async = [&](void* dst, const void* src) {
         const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+        // .ca (allocate in L1), not .cg: the two pixels of a step and the pixels of the next steps share half of their tap
+        // rows (the right taps of pixel x are the left taps of pixel x+1), so L1 serves ~4 of the 9 rows of a pixel and
+        // the L2 -> SM traffic drops accordingly (measured: 90 -> 85 us)
         if (kLaneBytes == 16)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
         else
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
     };

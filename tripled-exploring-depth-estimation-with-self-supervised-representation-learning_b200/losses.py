@@ -69,19 +69,57 @@ class LossDict(dict):
         for k, v in dict(*a, **kw).items():
             self[k] = v
 
+    _weights = {}                 # (device, ((numel, multiplicity), ...)) -> constant weight vector of the fused sum
+
+    def _fused_parts_sum(self):
+        """sum_i mult_i * sum(part_i) as ONE concatenation + ONE dot product (backward: one multiply, the parts' gradients
+        are contiguous slices of it) instead of a reduce / scale / add chain per part and an expand + copy per gradient:
+        the step is a serial chain of kernels, so each 2 us launch between the forward and the backward counts."""
+        parts = [(t.reshape(-1), m) for t, m, _ in self._parts]
+        dev = parts[0][0].device
+        if any(t.device != dev or t.dtype != torch.float32 for t, _ in parts):
+            return None
+        key = (dev, tuple((t.numel(), float(m)) for t, m in parts))
+        w = LossDict._weights.get(key)
+        if w is None:
+            if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+                return None       # (a host -> device copy cannot be captured; the eager warm-up steps fill the cache)
+            w = torch.tensor([m for t, m in parts for _ in range(t.numel())], dtype=torch.float32, device=dev)
+            LossDict._weights[key] = w
+        flat = torch.cat([t for t, _ in parts])
+        self._packed = flat.detach()
+        return torch.dot(flat, w)
+
+    def packed(self):
+        """After total(): every kernel-produced loss value in ONE device vector (the parts in registration order), for
+        logging with a single device->host copy instead of one ``.item()`` per entry (mono/apis/trainer.py:39-54);
+        None when total() did not take the fused path."""
+        return getattr(self, "_packed", None)
+
     def total(self):
         out = None
         covered = set()
+        fused = self._fused_parts_sum() if len(self._parts) > 1 else None
         for t, m, keys in self._parts:
+            covered.update(keys)
+            if fused is not None:
+                continue
             v = t.sum() if t.dim() else t
             v = v * m if m != 1 else v
             out = v if out is None else out + v
-            covered.update(keys)
+        if fused is not None:
+            out = fused
         for k, v in self.items():
             if k not in covered:
                 v = v.mean() if v.dim() else v
                 out = v if out is None else out + v
         return out
+
+
+def _scalar(t):
+    """0-dim VIEW of a one-element kernel output.  (``t[0]`` would do, but its backward materialises a zero vector and
+    copies the gradient into it: two launches per loss term on a step that is a serial chain of kernels.)"""
+    return t.reshape(())
 
 
 def _opt_get(opt, name, default=None):
@@ -216,7 +254,7 @@ class ViewSynthesisLossMixin:
         if cfg.materialize:
             for i, f in enumerate(frames):
                 outputs[("feature", f, 0)] = res[1 + i]
-        return res[0][0], (res[1 + len(frames)] if cfg.materialize else None)
+        return _scalar(res[0]), (res[1 + len(frames)] if cfg.materialize else None)
 
     def _extract(self, img):
         """``extractor(img)[0]`` (mono/model/mono_fm/net.py:113,197).  Encoders that can stop after their first
@@ -308,7 +346,7 @@ class ViewSynthesisLossMixin:
         for s in scales:
             res = outputs[("res_img", 0, s)]
             tgt_r = F.interpolate(target, list(res.shape[-2:]), mode="bilinear", align_corners=False)
-            loss_dict[("img_reconstruct_loss", s)] = MaskedReconstructionLoss.apply(1.0 / n, res, tgt_r, None)[0]
+            loss_dict[("img_reconstruct_loss", s)] = _scalar(MaskedReconstructionLoss.apply(1.0 / n, res, tgt_r, None))
             loss_dict[("min_reconstruct_loss", s)] = base[("min_reconstruct_loss", s)]
             loss_dict[("min_perceptional_loss", s)] = per
             loss_dict[("smooth_loss", s)] = base[("smooth_loss", s)]
@@ -341,7 +379,7 @@ class ViewSynthesisLossMixin:
                 size = list(res.shape[-2:])
                 tgt_r = F.interpolate(target, size, mode="bilinear", align_corners=False)
                 msk_r = F.interpolate(mask, size, mode="bilinear", align_corners=False)
-                rec = MaskedReconstructionLoss.apply(float(w_rec) / len(opt.scales), res, tgt_r, msk_r)[0]
+                rec = _scalar(MaskedReconstructionLoss.apply(float(w_rec) / len(opt.scales), res, tgt_r, msk_r))
                 loss_dict[("img_reconstruct_loss", s)] = rec
         base = self.compute_losses_baseline(inputs, outputs, noise)
         loss_dict.absorb(base)
@@ -372,4 +410,4 @@ class ViewSynthesisLossMixin:
     def get_feature_regularization_loss(self, feature, img):
         """mono/model/mono_fm_joint/net.py:309-330: -dis * first-order + cvt * second-order."""
         cfg = EdgeConfig(alpha=1.0, first_coef=-float(self.opt.dis), second_coef=float(self.opt.cvt))
-        return EdgeAwareSmoothness.apply(cfg, feature, img)[0]
+        return _scalar(EdgeAwareSmoothness.apply(cfg, feature, img))
