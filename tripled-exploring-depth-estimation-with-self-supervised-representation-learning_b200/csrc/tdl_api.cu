@@ -436,6 +436,9 @@ static int check_feat(const tdl_feat_args* a, bool bwd, FeatDev* d) {
     if (a->dtype != TDL_DTYPE_F32 && a->dtype != TDL_DTYPE_BF16) return TDL_ERR_SHAPE;
     if (a->dtype == TDL_DTYPE_BF16 && a->layout != TDL_LAYOUT_NHWC) return TDL_ERR_SHAPE;          // bf16 rows only
     if (a->layout == TDL_LAYOUT_NHWC && a->C % 4 != 0) return TDL_ERR_COUNT;
+    // the channel-last kernels index one image with 32-bit element offsets (pixel index also carries two flag bits)
+    if (a->layout == TDL_LAYOUT_NHWC && ((uint64_t)a->h * a->w * a->C >= (1ull << 31) || (uint64_t)a->h * a->w >= (1ull << 29)))
+        return TDL_ERR_SHAPE;
     d->layout = a->layout;
     d->dtype = a->dtype;
     d->tgt = static_cast<const float*>(a->tgt); d->disp = a->disp; d->P = a->P; d->invK = a->invK;

@@ -20,6 +20,11 @@
 namespace tdl {
 
 namespace f2 {
+template <typename P>
+TDL_DEV P* opaque(P* q) {                 // hides the pointer's provenance from the optimiser (see feat_fwd_nhwc_kernel)
+    asm volatile("" : "+l"(q));
+    return q;
+}
 constexpr int NT = 128;                 // 4 warps
 constexpr int PIX = 32;                 // pixels per warp
 
@@ -69,6 +74,7 @@ __global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) 
     const int b = blockIdx.y;
     const int h = p.h, w = p.w, C = p.C;
     const int hw = h * w;
+    const unsigned uC = (unsigned)C;
     if (tid < S * 12) s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
     if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
     __syncthreads();
@@ -95,13 +101,15 @@ __global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) 
     //      samples on the first use of a row, 22 % warps active at 126 registers), and data in flight in shared memory
     //      costs no registers.  Each lane reads back exactly the bytes it copied, so no barrier is needed -- only the
     //      cp.async group wait.
-    const T* __restrict__ tgt = reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C;
+    // (image base pointers as opaque per-thread registers: left symbolic, the compiler re-adds the uniform 64-bit image
+    //  offset to every row address -- four instructions per address instead of one widening multiply-add)
+    const T* __restrict__ tgt = opaque(reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C);
     const T* __restrict__ srcb[S];
     T* __restrict__ wrpb[S];
 #pragma unroll
     for (int f = 0; f < S; ++f) {
-        srcb[f] = reinterpret_cast<const T*>(p.src[f]) + (size_t)b * hw * C;
-        wrpb[f] = p.warped[f] ? reinterpret_cast<T*>(p.warped[f]) + (size_t)b * hw * C : nullptr;
+        srcb[f] = opaque(reinterpret_cast<const T*>(p.src[f]) + (size_t)b * hw * C);
+        wrpb[f] = p.warped[f] ? opaque(reinterpret_cast<T*>(p.warped[f]) + (size_t)b * hw * C) : nullptr;
     }
     constexpr int kStages = 3;
     constexpr int kRowsPerStep = 1 + 4 * S;
@@ -126,18 +134,21 @@ __global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) 
         const int pl = q + half;
         const int pix = min(pix0 + pl, hw - 1);
         const int c = min(cl + 64 * ck, C - 4);
-        cp_async(slot(stage, 0), tgt + (size_t)pix * C + c);
+        cp_async(slot(stage, 0), tgt + ((unsigned)pix * uC + (unsigned)c));
 #pragma unroll
         for (int f = 0; f < S; ++f) {
             const Tap tp = s_tap[wq][pl][f];
             const int o = tp.o00 & 0x1fffffff;
             const int dx = (tp.o00 >> 30) & 1, dy = ((tp.o00 >> 29) & 1) ? w : 0;
             // a clamped tap has weight exactly 0, so loading the clamped row adds 0 like ATen's skipped tap
-            const T* sb = srcb[f] + c;
-            cp_async(slot(stage, 1 + 4 * f + 0), sb + (size_t)o * C);
-            cp_async(slot(stage, 1 + 4 * f + 1), sb + (size_t)(o + dx) * C);
-            cp_async(slot(stage, 1 + 4 * f + 2), sb + (size_t)(o + dy) * C);
-            cp_async(slot(stage, 1 + 4 * f + 3), sb + (size_t)(o + dy + dx) * C);
+            // (element offsets inside one image fit 32 bits -- checked by the API -- so an address is one 32-bit
+            //  multiply-add and one widening add instead of a 64-bit product per row: the kernel is issue-bound)
+            const T* sb = srcb[f];
+            const unsigned e00 = (unsigned)o * uC + (unsigned)c, ex = dx ? uC : 0u, ey = (unsigned)dy * uC;
+            cp_async(slot(stage, 1 + 4 * f + 0), sb + e00);
+            cp_async(slot(stage, 1 + 4 * f + 1), sb + (e00 + ex));
+            cp_async(slot(stage, 1 + 4 * f + 2), sb + (e00 + ey));
+            cp_async(slot(stage, 1 + 4 * f + 3), sb + (e00 + ey + ex));
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -190,7 +201,7 @@ __global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) 
                     v.y = a.y * tp.nw + bq.y * tp.ne + cq.y * tp.sw + d.y * tp.se;
                     v.z = a.z * tp.nw + bq.z * tp.ne + cq.z * tp.sw + d.z * tp.se;
                     v.w = a.w * tp.nw + bq.w * tp.ne + cq.w * tp.sw + d.w * tp.se;
-                    if (wrpb[f]) st4(wrpb[f] + (size_t)pix * C + c, v);
+                    if (wrpb[f]) st4(wrpb[f] + ((unsigned)pix * uC + (unsigned)c), v);
                     const float e0 = v.x - t.x, e1 = v.y - t.y, e2 = v.z - t.z, e3 = v.w - t.w;      // robust_l1(tgt_f, src_f)
                     acc[f] += sqrt_fast(fmaf(e0, e0, kL1Eps2)) + sqrt_fast(fmaf(e1, e1, kL1Eps2)) +
                               sqrt_fast(fmaf(e2, e2, kL1Eps2)) + sqrt_fast(fmaf(e3, e3, kL1Eps2));
@@ -294,9 +305,9 @@ __global__ void __launch_bounds__(f2::NT) feat_bwd_nhwc_kernel(const FeatDev p) 
     __syncwarp();
     // ---- phase 2: two pixels per step
     const float up = __ldg(p.dloss) * p.coef / ((float)p.Bnorm * (float)h * (float)w) / (float)C;
-    const T* __restrict__ tgt = reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C;
-    T* __restrict__ dtg = p.d_tgt ? reinterpret_cast<T*>(p.d_tgt) + (size_t)b * hw * C : nullptr;
-    T* Gb = (kGrad && !p.d_tgt) ? reinterpret_cast<T*>(p.G) + (size_t)b * hw * C : nullptr;
+    const T* __restrict__ tgt = opaque(reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C);
+    T* __restrict__ dtg = p.d_tgt ? opaque(reinterpret_cast<T*>(p.d_tgt) + (size_t)b * hw * C) : nullptr;
+    T* Gb = (kGrad && !p.d_tgt) ? opaque(reinterpret_cast<T*>(p.G) + (size_t)b * hw * C) : nullptr;
     // the five rows of a pixel (target + 4 taps of its arg-min frame) are requested one step ahead of the arithmetic
     struct Rows {
         float4 t, a, bq, cq, d;
@@ -309,14 +320,16 @@ __global__ void __launch_bounds__(f2::NT) feat_bwd_nhwc_kernel(const FeatDev p) 
 #pragma unroll
         for (int f = 1; f < TDL_MAX_SRC; ++f)
             if (f == fs) sbf = p.src[f];
-        const T* sb = reinterpret_cast<const T*>(sbf) + (size_t)b * hw * C + c;
+        const T* sb = opaque(reinterpret_cast<const T*>(sbf) + (size_t)b * hw * C);
         const int o = tp.o00 & 0x1fffffff;
         const int dx = (tp.o00 >> 30) & 1, dy = ((tp.o00 >> 29) & 1) ? w : 0;
-        r.t = ld4(tgt + (size_t)pix * C + c);
-        r.a = ld4(sb + (size_t)o * C);
-        r.bq = ld4(sb + (size_t)(o + dx) * C);
-        r.cq = ld4(sb + (size_t)(o + dy) * C);
-        r.d = ld4(sb + (size_t)(o + dy + dx) * C);
+        // (32-bit element offsets inside one image, see feat_fwd_nhwc_kernel)
+        const unsigned uC = (unsigned)C, e00 = (unsigned)o * uC + (unsigned)c, ex = dx ? uC : 0u, ey = (unsigned)dy * uC;
+        r.t = ld4(tgt + ((unsigned)pix * uC + (unsigned)c));
+        r.a = ld4(sb + e00);
+        r.bq = ld4(sb + (e00 + ex));
+        r.cq = ld4(sb + (e00 + ey));
+        r.d = ld4(sb + (e00 + ey + ex));
     };
     const int nchunk = (C + 63) / 64;
     const int nsteps = (PIX / 2) * nchunk;
@@ -355,8 +368,9 @@ __global__ void __launch_bounds__(f2::NT) feat_bwd_nhwc_kernel(const FeatDev p) 
             chan(a.y, bq.y, cq.y, d.y, t.y, gq.y);
             chan(a.z, bq.z, cq.z, d.z, t.z, gq.z);
             chan(a.w, bq.w, cq.w, d.w, t.w, gq.w);
-            if (dtg) st4(dtg + (size_t)pix * C + c, make_float4(-gq.x, -gq.y, -gq.z, -gq.w));
-            if (Gb) st4(Gb + (size_t)pix * C + c, gq);
+            const unsigned eo = (unsigned)pix * (unsigned)C + (unsigned)c;
+            if (dtg) st4(dtg + eo, make_float4(-gq.x, -gq.y, -gq.z, -gq.w));
+            if (Gb) st4(Gb + eo, gq);
         }
         if (ck == nchunk - 1) {
 #pragma unroll
@@ -450,13 +464,13 @@ __global__ void __launch_bounds__(f2::NT) feat_gather_nhwc_kernel(const FeatDev 
     }
     __syncwarp();
     const bool from_dtgt = p.d_tgt != nullptr;               // g = -d_tgt
-    const T* Gb = reinterpret_cast<const T*>(from_dtgt ? p.d_tgt : p.G) + (size_t)b * hw * C;
+    const T* Gb = opaque(reinterpret_cast<const T*>(from_dtgt ? p.d_tgt : p.G) + (size_t)b * hw * C);
     const float sgn = from_dtgt ? -1.f : 1.f;
     float* dsf = p.d_src[0];
 #pragma unroll
     for (int k = 1; k < TDL_MAX_SRC; ++k)
         if (k == f) dsf = p.d_src[k];
-    T* dst = reinterpret_cast<T*>(dsf) + (size_t)b * hw * C;
+    T* dst = opaque(reinterpret_cast<T*>(dsf) + (size_t)b * hw * C);
     for (int q = 0; q < PIX; q += 2) {
         const int pl = q + half;
         const int o = o0 + pl;
@@ -471,7 +485,7 @@ __global__ void __launch_bounds__(f2::NT) feat_gather_nhwc_kernel(const FeatDev 
                 if (k < n) {
                     const int2 e = s_ent[wq][pl][k];
                     wgt[k] = sgn * __int_as_float(e.y);
-                    rows[k] = ld4(Gb + (size_t)e.x * C + c);
+                    rows[k] = ld4(Gb + ((unsigned)e.x * (unsigned)C + (unsigned)c));
                 }
             }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -484,7 +498,7 @@ __global__ void __launch_bounds__(f2::NT) feat_gather_nhwc_kernel(const FeatDev 
                     acc.w = fmaf(wgt[k], rows[k].w, acc.w);
                 }
             }
-            st4(dst + (size_t)o * C + c, acc);
+            st4(dst + ((unsigned)o * (unsigned)C + (unsigned)c), acc);
         }
     }
 }
