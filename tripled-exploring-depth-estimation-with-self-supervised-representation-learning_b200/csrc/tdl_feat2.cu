@@ -12,6 +12,8 @@
 // Thread mapping (all three kernels): a warp owns 32 consecutive pixels.  Phase 1, lane = pixel: projection, taps,
 // bucket registration -- scalar per-pixel work, parked in shared memory.  Phase 2, two pixels at a time: each half-warp
 // takes one pixel, lane l of the half owns channels 4l .. 4l+3 of a 64-channel chunk (one 16-byte / 8-byte access per row).
+#include <type_traits>
+
 #include "tdl_common.cuh"
 #include "tdl_internal.h"
 
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) 
         wrpb[f] = p.warped[f] ? opaque(reinterpret_cast<T*>(p.warped[f]) + (size_t)b * hw * C) : nullptr;
     }
     constexpr int kStages = 3;
+    static_assert(kStages == 3, "the step loop below is unrolled by three");
     constexpr int kRowsPerStep = 1 + 4 * S;
     constexpr int kLaneBytes = 4 * (int)sizeof(T);          // 16 (fp32) or 8 (bf16) bytes per lane and row
     extern __shared__ __align__(16) unsigned char s_ring_raw[];
@@ -176,46 +179,58 @@ __global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) 
         else asm volatile("cp.async.commit_group;" ::: "memory");
         advance(iq, ick);
     }
-    int stage = 0;
-    for (int q = 0; q < PIX; q += 2) {
+    // One step with a COMPILE-TIME ring stage (the loop below is unrolled by kStages): every shared-memory slot address is
+    // then a constant offset from one per-lane register instead of index arithmetic per row.
+    auto step = [&](auto stage_c, int q, int ck) {
+        constexpr int stage = decltype(stage_c)::value;
         const int pl = q + half;
         const int pix = pix0 + pl;
-        for (int ck = 0; ck < nchunk; ++ck) {
-            // request step + (kStages - 1) into the slot consumed in the previous iteration, then wait for this step's group
-            {
-                const int st_next = stage == 0 ? kStages - 1 : stage - 1;
-                if (iq < PIX) issue(iq, ick, st_next);
-                else asm volatile("cp.async.commit_group;" ::: "memory");
-                advance(iq, ick);
-            }
-            asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
-            const int c = cl + 64 * ck;
-            if (pix < hw && c < C) {
-                const float4 t = rd(stage, 0);
+        // request step + (kStages - 1) into the slot consumed in the previous step, then wait for this step's group
+        if (iq < PIX) issue(iq, ick, (stage + kStages - 1) % kStages);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        advance(iq, ick);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
+        const int c = cl + 64 * ck;
+        if (pix < hw && c < C) {
+            const float4 t = rd(stage, 0);
 #pragma unroll
-                for (int f = 0; f < S; ++f) {
-                    const Tap tp = s_tap[wq][pl][f];
-                    const float4 a = rd(stage, 1 + 4 * f), bq = rd(stage, 2 + 4 * f), cq = rd(stage, 3 + 4 * f), d = rd(stage, 4 + 4 * f);
-                    float4 v;
-                    v.x = a.x * tp.nw + bq.x * tp.ne + cq.x * tp.sw + d.x * tp.se;
-                    v.y = a.y * tp.nw + bq.y * tp.ne + cq.y * tp.sw + d.y * tp.se;
-                    v.z = a.z * tp.nw + bq.z * tp.ne + cq.z * tp.sw + d.z * tp.se;
-                    v.w = a.w * tp.nw + bq.w * tp.ne + cq.w * tp.sw + d.w * tp.se;
-                    if (wrpb[f]) st4(wrpb[f] + ((unsigned)pix * uC + (unsigned)c), v);
-                    const float e0 = v.x - t.x, e1 = v.y - t.y, e2 = v.z - t.z, e3 = v.w - t.w;      // robust_l1(tgt_f, src_f)
-                    acc[f] += sqrt_fast(fmaf(e0, e0, kL1Eps2)) + sqrt_fast(fmaf(e1, e1, kL1Eps2)) +
-                              sqrt_fast(fmaf(e2, e2, kL1Eps2)) + sqrt_fast(fmaf(e3, e3, kL1Eps2));
-                }
+            for (int f = 0; f < S; ++f) {
+                const Tap tp = s_tap[wq][pl][f];
+                const float4 a = rd(stage, 1 + 4 * f), bq = rd(stage, 2 + 4 * f), cq = rd(stage, 3 + 4 * f), d = rd(stage, 4 + 4 * f);
+                float4 v;
+                v.x = a.x * tp.nw + bq.x * tp.ne + cq.x * tp.sw + d.x * tp.se;
+                v.y = a.y * tp.nw + bq.y * tp.ne + cq.y * tp.sw + d.y * tp.se;
+                v.z = a.z * tp.nw + bq.z * tp.ne + cq.z * tp.sw + d.z * tp.se;
+                v.w = a.w * tp.nw + bq.w * tp.ne + cq.w * tp.sw + d.w * tp.se;
+                if (wrpb[f]) st4(wrpb[f] + ((unsigned)pix * uC + (unsigned)c), v);
+                const float e0 = v.x - t.x, e1 = v.y - t.y, e2 = v.z - t.z, e3 = v.w - t.w;      // robust_l1(tgt_f, src_f)
+                // sqrt(t) as t * rsqrt(t): 2 ulp, zero-mean -- 3 instructions per channel instead of 6 for the refined
+                // root; the sum over C channels and the mean over pixels stay well inside the 1e-5 parity bound
+                const float t0 = fmaf(e0, e0, kL1Eps2), t1 = fmaf(e1, e1, kL1Eps2), t2 = fmaf(e2, e2, kL1Eps2), t3 = fmaf(e3, e3, kL1Eps2);
+                acc[f] += (t0 * rsqrt_approx(t0) + t1 * rsqrt_approx(t1)) + (t2 * rsqrt_approx(t2) + t3 * rsqrt_approx(t3));
             }
-            stage = stage + 1 == kStages ? 0 : stage + 1;
         }
-        // all chunks of this pixel pair done: reduce over the 16 lanes
+        if (ck == nchunk - 1) {                              // all chunks of this pixel pair done: reduce over the 16 lanes
 #pragma unroll
-        for (int f = 0; f < S; ++f) {
+            for (int f = 0; f < S; ++f) {
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], o);
-            if (l16 == 0) s_res[wq][pl][f] = acc[f];
-            acc[f] = 0.f;
+                for (int o = 8; o > 0; o >>= 1) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], o);
+                if (l16 == 0) s_res[wq][pl][f] = acc[f];
+                acc[f] = 0.f;
+            }
+        }
+    };
+    {
+        int q = 0, ck = 0;
+        while (q < PIX) {
+            step(std::integral_constant<int, 0>{}, q, ck);
+            advance(q, ck);
+            if (q >= PIX) break;
+            step(std::integral_constant<int, 1>{}, q, ck);
+            advance(q, ck);
+            if (q >= PIX) break;
+            step(std::integral_constant<int, 2>{}, q, ck);
+            advance(q, ck);
         }
     }
     __syncwarp();
@@ -335,14 +350,16 @@ __global__ void __launch_bounds__(f2::NT) feat_bwd_nhwc_kernel(const FeatDev p) 
     const int nsteps = (PIX / 2) * nchunk;
     const int cl = 4 * l16;
     float gix = 0.f, giy = 0.f;
-    auto step = [&](int it, Rows& cur, Rows& nxt) {           // two register sets alternate, see feat_fwd_nhwc_kernel
-        const int q = (it / nchunk) * 2, ck = it - (it / nchunk) * nchunk;
+    int sq = 0, sck = 0;                                       // (pixel pair, chunk) of the current step: advanced, never divided
+    auto step = [&](Rows& cur, Rows& nxt) {                   // two register sets alternate, see feat_fwd_nhwc_kernel
+        const int q = sq, ck = sck;
         const int pl = q + half, c = cl + 64 * ck;
         const int pix = pix0 + pl;
-        if (it + 1 < nsteps) {
-            const int q2 = ((it + 1) / nchunk) * 2, ck2 = (it + 1) - ((it + 1) / nchunk) * nchunk;
-            fetch(q2 + half, min(cl + 64 * ck2, C - 4), nxt);
+        if (++sck == nchunk) {
+            sck = 0;
+            sq += 2;
         }
+        if (sq < PIX) fetch(sq + half, min(cl + 64 * sck, C - 4), nxt);
         if (pix < hw && c < C) {
             const Tap tp = s_tap[wq][pl];
             const bool vx = (tp.o00 >> 30) & 1, vy = (tp.o00 >> 29) & 1;
@@ -385,9 +402,9 @@ __global__ void __launch_bounds__(f2::NT) feat_bwd_nhwc_kernel(const FeatDev p) 
     {
         Rows ra, rb;
         fetch(half, min(cl, C - 4), ra);
-        for (int it = 0; it < nsteps; it += 2) {
-            step(it, ra, rb);
-            step(it + 1, rb, ra);
+        for (int it = 0; it < nsteps; it += 2) {              // (nsteps = 16 * nchunk is even)
+            step(ra, rb);
+            step(rb, ra);
         }
     }
     __syncwarp();
@@ -474,28 +491,42 @@ __global__ void __launch_bounds__(f2::NT) feat_gather_nhwc_kernel(const FeatDev 
     for (int q = 0; q < PIX; q += 2) {
         const int pl = q + half;
         const int o = o0 + pl;
+        const int n = o < hw ? s_n[wq][pl] : 0;
+        // the slots are walked in pairs up to the larger count of the warp's two pixels (warp-uniform branches): with the
+        // typical 2-4 registered taps per source pixel, predicated-off instructions of the unused slots were most of what
+        // this kernel issued (it ran at 66 % issue utilisation)
+        const int nmax = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
         if (o >= hw) continue;
-        const int n = s_n[wq][pl];
         for (int c = 4 * l16; c < C; c += 64) {
             // the rows of the registered taps only (n is the same for the 16 lanes of a pixel), all requested before the first use
             float4 rows[kFeatBucketCap];
             float wgt[kFeatBucketCap];
 #pragma unroll
-            for (int k = 0; k < kFeatBucketCap; ++k) {
-                if (k < n) {
-                    const int2 e = s_ent[wq][pl][k];
-                    wgt[k] = sgn * __int_as_float(e.y);
-                    rows[k] = ld4(Gb + ((unsigned)e.x * (unsigned)C + (unsigned)c));
+            for (int k0 = 0; k0 < kFeatBucketCap; k0 += 2) {
+                if (k0 < nmax) {
+#pragma unroll
+                    for (int k = k0; k < k0 + 2; ++k) {
+                        if (k < n) {
+                            const int2 e = s_ent[wq][pl][k];
+                            wgt[k] = sgn * __int_as_float(e.y);
+                            rows[k] = ld4(Gb + ((unsigned)e.x * (unsigned)C + (unsigned)c));
+                        }
+                    }
                 }
             }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < kFeatBucketCap; ++k) {
-                if (k < n) {
-                    acc.x = fmaf(wgt[k], rows[k].x, acc.x);
-                    acc.y = fmaf(wgt[k], rows[k].y, acc.y);
-                    acc.z = fmaf(wgt[k], rows[k].z, acc.z);
-                    acc.w = fmaf(wgt[k], rows[k].w, acc.w);
+            for (int k0 = 0; k0 < kFeatBucketCap; k0 += 2) {
+                if (k0 < nmax) {
+#pragma unroll
+                    for (int k = k0; k < k0 + 2; ++k) {
+                        if (k < n) {
+                            acc.x = fmaf(wgt[k], rows[k].x, acc.x);
+                            acc.y = fmaf(wgt[k], rows[k].y, acc.y);
+                            acc.z = fmaf(wgt[k], rows[k].z, acc.z);
+                            acc.w = fmaf(wgt[k], rows[k].w, acc.w);
+                        }
+                    }
                 }
             }
             st4(dst + ((unsigned)o * (unsigned)C + (unsigned)c), acc);
