@@ -323,50 +323,87 @@ __global__ void __launch_bounds__(f2::NT) feat_bwd_nhwc_kernel(const FeatDev p) 
     const T* __restrict__ tgt = opaque(reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C);
     T* __restrict__ dtg = p.d_tgt ? opaque(reinterpret_cast<T*>(p.d_tgt) + (size_t)b * hw * C) : nullptr;
     T* Gb = (kGrad && !p.d_tgt) ? opaque(reinterpret_cast<T*>(p.G) + (size_t)b * hw * C) : nullptr;
-    // the five rows of a pixel (target + 4 taps of its arg-min frame) are requested one step ahead of the arithmetic
-    struct Rows {
-        float4 t, a, bq, cq, d;
+    // The five rows of a pixel (target + 4 taps of its arg-min frame) travel global -> shared memory with cp.async,
+    // kStages - 1 steps ahead of the arithmetic (a compile-time ring stage per unrolled step, as in feat_fwd_nhwc_kernel):
+    // with one step of register prefetch the kernel waited on these loads (long-scoreboard stall 4.6 per issue) at 96
+    // registers; data in flight in shared memory costs none.  Each lane reads back the bytes it copied: no barrier.
+    constexpr int kStages = 4;
+    constexpr int kRowsPerStep = 5;
+    constexpr int kLaneBytes = 4 * (int)sizeof(T);
+    extern __shared__ __align__(16) unsigned char s_ring_raw[];
+    unsigned char* ring = s_ring_raw + (size_t)wq * kStages * kRowsPerStep * 32 * kLaneBytes + (size_t)lane * kLaneBytes;
+    auto slot = [&](int stage, int row) { return ring + (size_t)(stage * kRowsPerStep + row) * 32 * kLaneBytes; };
+    auto cp_async = [&](void* dst, const void* src) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+        if (kLaneBytes == 16)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+        else
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
     };
-    auto fetch = [&](int pl, int c, Rows& r) {
+    auto rd = [&](int stage, int row) -> float4 {
+        const unsigned char* q = slot(stage, row);
+        if (sizeof(T) == 4) return *reinterpret_cast<const float4*>(q);
+        const uint2 u = *reinterpret_cast<const uint2*>(q);
+        return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                           __uint_as_float(u.y & 0xffff0000u));
+    };
+    const T* __restrict__ srcb[TDL_MAX_SRC];
+#pragma unroll
+    for (int f = 0; f < TDL_MAX_SRC; ++f)
+        srcb[f] = f < S ? opaque(reinterpret_cast<const T*>(p.src[f]) + (size_t)b * hw * C) : nullptr;
+    const int nchunk = (C + 63) / 64;
+    const int cl = 4 * l16;
+    const unsigned uC = (unsigned)C;
+    auto issue = [&](int q, int ck, int stage) {
+        const int pl = q + half;
         const int pix = min(pix0 + pl, hw - 1);
+        const unsigned c = (unsigned)min(cl + 64 * ck, C - 4);
         const Tap tp = s_tap[wq][pl];
         const int fs = s_fs[wq][pl];
-        const float* sbf = p.src[0];
+        const T* sb = srcb[0];
 #pragma unroll
         for (int f = 1; f < TDL_MAX_SRC; ++f)
-            if (f == fs) sbf = p.src[f];
-        const T* sb = opaque(reinterpret_cast<const T*>(sbf) + (size_t)b * hw * C);
+            if (f == fs) sb = srcb[f];
         const int o = tp.o00 & 0x1fffffff;
         const int dx = (tp.o00 >> 30) & 1, dy = ((tp.o00 >> 29) & 1) ? w : 0;
-        // (32-bit element offsets inside one image, see feat_fwd_nhwc_kernel)
-        const unsigned uC = (unsigned)C, e00 = (unsigned)o * uC + (unsigned)c, ex = dx ? uC : 0u, ey = (unsigned)dy * uC;
-        r.t = ld4(tgt + ((unsigned)pix * uC + (unsigned)c));
-        r.a = ld4(sb + e00);
-        r.bq = ld4(sb + (e00 + ex));
-        r.cq = ld4(sb + (e00 + ey));
-        r.d = ld4(sb + (e00 + ey + ex));
+        // (32-bit element offsets inside one image, see feat_fwd_nhwc_kernel; a clamped tap re-reads a valid row)
+        const unsigned e00 = (unsigned)o * uC + c, ex = dx ? uC : 0u, ey = (unsigned)dy * uC;
+        cp_async(slot(stage, 0), tgt + ((unsigned)pix * uC + c));
+        cp_async(slot(stage, 1), sb + e00);
+        cp_async(slot(stage, 2), sb + (e00 + ex));
+        cp_async(slot(stage, 3), sb + (e00 + ey));
+        cp_async(slot(stage, 4), sb + (e00 + ey + ex));
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    const int nchunk = (C + 63) / 64;
-    const int nsteps = (PIX / 2) * nchunk;
-    const int cl = 4 * l16;
+    int iq = 0, ick = 0;                                     // (pixel pair, chunk) of the next step to request
+    auto advance = [&](int& q, int& ck) {
+        if (++ck == nchunk) {
+            ck = 0;
+            q += 2;
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < kStages - 1; ++k) {
+        if (iq < PIX) issue(iq, ick, k);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        advance(iq, ick);
+    }
     float gix = 0.f, giy = 0.f;
-    int sq = 0, sck = 0;                                       // (pixel pair, chunk) of the current step: advanced, never divided
-    auto step = [&](Rows& cur, Rows& nxt) {                   // two register sets alternate, see feat_fwd_nhwc_kernel
-        const int q = sq, ck = sck;
+    auto step = [&](auto stage_c, int q, int ck) {
+        constexpr int stage = decltype(stage_c)::value;
         const int pl = q + half, c = cl + 64 * ck;
         const int pix = pix0 + pl;
-        if (++sck == nchunk) {
-            sck = 0;
-            sq += 2;
-        }
-        if (sq < PIX) fetch(sq + half, min(cl + 64 * sck, C - 4), nxt);
+        if (iq < PIX) issue(iq, ick, (stage + kStages - 1) % kStages);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        advance(iq, ick);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
         if (pix < hw && c < C) {
             const Tap tp = s_tap[wq][pl];
             const bool vx = (tp.o00 >> 30) & 1, vy = (tp.o00 >> 29) & 1;
             // weights back to the fractions: nw = ex*ey, ne = ax*ey, sw = ex*ay, se = ax*ay with ex + ax = ey + ay = 1
             const float ax = tp.ne + tp.se, ay = tp.sw + tp.se, ex = tp.nw + tp.sw, ey = tp.nw + tp.ne;
-            float4 a = cur.a, bq = cur.bq, cq = cur.cq, d = cur.d;
-            const float4 t = cur.t;
+            float4 a = rd(stage, 1), bq = rd(stage, 2), cq = rd(stage, 3), d = rd(stage, 4);
+            const float4 t = rd(stage, 0);
             if (!vx) bq = d = make_float4(0.f, 0.f, 0.f, 0.f);           // ATen skips the out-of-range taps
             if (!vy) cq = make_float4(0.f, 0.f, 0.f, 0.f);
             if (!vy) d = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -385,7 +422,7 @@ __global__ void __launch_bounds__(f2::NT) feat_bwd_nhwc_kernel(const FeatDev p) 
             chan(a.y, bq.y, cq.y, d.y, t.y, gq.y);
             chan(a.z, bq.z, cq.z, d.z, t.z, gq.z);
             chan(a.w, bq.w, cq.w, d.w, t.w, gq.w);
-            const unsigned eo = (unsigned)pix * (unsigned)C + (unsigned)c;
+            const unsigned eo = (unsigned)pix * uC + (unsigned)c;
             if (dtg) st4(dtg + eo, make_float4(-gq.x, -gq.y, -gq.z, -gq.w));
             if (Gb) st4(Gb + eo, gq);
         }
@@ -400,11 +437,17 @@ __global__ void __launch_bounds__(f2::NT) feat_bwd_nhwc_kernel(const FeatDev p) 
         }
     };
     {
-        Rows ra, rb;
-        fetch(half, min(cl, C - 4), ra);
-        for (int it = 0; it < nsteps; it += 2) {              // (nsteps = 16 * nchunk is even)
-            step(ra, rb);
-            step(rb, ra);
+        static_assert(kStages == 4, "the step loop is unrolled by four");
+        int q = 0, ck = 0;
+        while (q < PIX) {                                    // 16 * nchunk steps: a multiple of four
+            step(std::integral_constant<int, 0>{}, q, ck);
+            advance(q, ck);
+            step(std::integral_constant<int, 1>{}, q, ck);
+            advance(q, ck);
+            step(std::integral_constant<int, 2>{}, q, ck);
+            advance(q, ck);
+            step(std::integral_constant<int, 3>{}, q, ck);
+            advance(q, ck);
         }
     }
     __syncwarp();
@@ -599,18 +642,22 @@ cudaError_t launch_feat_fwd_nhwc(const FeatDev& p, cudaStream_t st) {
     return p.dtype == TDL_DTYPE_BF16 ? fwd_t<__nv_bfloat16>(p, st) : fwd_t<float>(p, st);
 }
 
-cudaError_t launch_feat_bwd_nhwc(const FeatDev& p, cudaStream_t st) {
+template <bool kGrad, typename T>
+static cudaError_t bwd_nhwc_t(const FeatDev& p, cudaStream_t st) {
     using namespace f2;
+    // cp.async ring: 4 stages x 5 rows x 32 lanes x (16 | 8) bytes per warp
+    const size_t smem = (size_t)(NT / 32) * 4 * 5 * 32 * 4 * sizeof(T);
+    static SmemOptIn opt_in;
+    if (cudaError_t e = opt_in(feat_bwd_nhwc_kernel<kGrad, T>, smem)) return e;
     dim3 grid((unsigned)((p.h * p.w + NT - 1) / NT), p.B);
-    const bool grad = p.bk_cnt != nullptr;                   // d_src requested: register taps for the gather
-    if (p.dtype == TDL_DTYPE_BF16) {
-        if (grad) feat_bwd_nhwc_kernel<true, __nv_bfloat16><<<grid, NT, 0, st>>>(p);
-        else feat_bwd_nhwc_kernel<false, __nv_bfloat16><<<grid, NT, 0, st>>>(p);
-    } else {
-        if (grad) feat_bwd_nhwc_kernel<true, float><<<grid, NT, 0, st>>>(p);
-        else feat_bwd_nhwc_kernel<false, float><<<grid, NT, 0, st>>>(p);
-    }
+    feat_bwd_nhwc_kernel<kGrad, T><<<grid, NT, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t launch_feat_bwd_nhwc(const FeatDev& p, cudaStream_t st) {
+    const bool grad = p.bk_cnt != nullptr;                   // d_src requested: register taps for the gather
+    if (p.dtype == TDL_DTYPE_BF16) return grad ? bwd_nhwc_t<true, __nv_bfloat16>(p, st) : bwd_nhwc_t<false, __nv_bfloat16>(p, st);
+    return grad ? bwd_nhwc_t<true, float>(p, st) : bwd_nhwc_t<false, float>(p, st);
 }
 
 cudaError_t launch_feat_gather_nhwc(const FeatDev& p, cudaStream_t st) {
