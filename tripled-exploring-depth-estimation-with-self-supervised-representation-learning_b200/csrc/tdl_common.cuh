@@ -238,6 +238,15 @@ TDL_DEV Bilin bilin_taps(float ix, float iy, int H, int W) {
 // one channel plane; returns the interpolated value.  The east / south taps are loaded from a clamped
 // index: a clamped tap always has weight exactly 0 (ix == W-1 or iy == H-1 after border clipping), so it
 // adds 0 like ATen's skipped out-of-range tap, without predicated loads or branches.
+// Hides a pointer's provenance from the optimiser.  Left symbolic, "kernel-parameter base + uniform 64-bit image offset +
+// per-thread index" is re-assembled for every access (add, add-with-carry, shift-add pair); an opaque per-thread base
+// register makes each access one widening multiply-add of the 32-bit element index.
+template <typename P>
+TDL_DEV P* opaque(P* q) {
+    asm volatile("" : "+l"(q));
+    return q;
+}
+
 TDL_DEV float bilin_sample(const float* __restrict__ plane, int W, const Bilin& t) {
     const float* p = plane + (size_t)t.y0 * W + t.x0;
     const int dx = t.vx ? 1 : 0, dy = t.vy ? W : 0;

@@ -22,11 +22,6 @@
 namespace tdl {
 
 namespace f2 {
-template <typename P>
-TDL_DEV P* opaque(P* q) {                 // hides the pointer's provenance from the optimiser (see feat_fwd_nhwc_kernel)
-    asm volatile("" : "+l"(q));
-    return q;
-}
 constexpr int NT = 128;                 // 4 warps
 constexpr int PIX = 32;                 // pixels per warp
 
@@ -105,13 +100,13 @@ __global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) 
     //      cp.async group wait.
     // (image base pointers as opaque per-thread registers: left symbolic, the compiler re-adds the uniform 64-bit image
     //  offset to every row address -- four instructions per address instead of one widening multiply-add)
-    const T* __restrict__ tgt = opaque(reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C);
+    const T* __restrict__ tgt = tdl::opaque(reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C);
     const T* __restrict__ srcb[S];
     T* __restrict__ wrpb[S];
 #pragma unroll
     for (int f = 0; f < S; ++f) {
-        srcb[f] = opaque(reinterpret_cast<const T*>(p.src[f]) + (size_t)b * hw * C);
-        wrpb[f] = p.warped[f] ? opaque(reinterpret_cast<T*>(p.warped[f]) + (size_t)b * hw * C) : nullptr;
+        srcb[f] = tdl::opaque(reinterpret_cast<const T*>(p.src[f]) + (size_t)b * hw * C);
+        wrpb[f] = p.warped[f] ? tdl::opaque(reinterpret_cast<T*>(p.warped[f]) + (size_t)b * hw * C) : nullptr;
     }
     constexpr int kStages = 3;
     static_assert(kStages == 3, "the step loop below is unrolled by three");
@@ -320,9 +315,9 @@ __global__ void __launch_bounds__(f2::NT) feat_bwd_nhwc_kernel(const FeatDev p) 
     __syncwarp();
     // ---- phase 2: two pixels per step
     const float up = __ldg(p.dloss) * p.coef / ((float)p.Bnorm * (float)h * (float)w) / (float)C;
-    const T* __restrict__ tgt = opaque(reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C);
-    T* __restrict__ dtg = p.d_tgt ? opaque(reinterpret_cast<T*>(p.d_tgt) + (size_t)b * hw * C) : nullptr;
-    T* Gb = (kGrad && !p.d_tgt) ? opaque(reinterpret_cast<T*>(p.G) + (size_t)b * hw * C) : nullptr;
+    const T* __restrict__ tgt = tdl::opaque(reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C);
+    T* __restrict__ dtg = p.d_tgt ? tdl::opaque(reinterpret_cast<T*>(p.d_tgt) + (size_t)b * hw * C) : nullptr;
+    T* Gb = (kGrad && !p.d_tgt) ? tdl::opaque(reinterpret_cast<T*>(p.G) + (size_t)b * hw * C) : nullptr;
     // The five rows of a pixel (target + 4 taps of its arg-min frame) travel global -> shared memory with cp.async,
     // kStages - 1 steps ahead of the arithmetic (a compile-time ring stage per unrolled step, as in feat_fwd_nhwc_kernel):
     // with one step of register prefetch the kernel waited on these loads (long-scoreboard stall 4.6 per issue) at 96
@@ -350,7 +345,7 @@ __global__ void __launch_bounds__(f2::NT) feat_bwd_nhwc_kernel(const FeatDev p) 
     const T* __restrict__ srcb[TDL_MAX_SRC];
 #pragma unroll
     for (int f = 0; f < TDL_MAX_SRC; ++f)
-        srcb[f] = f < S ? opaque(reinterpret_cast<const T*>(p.src[f]) + (size_t)b * hw * C) : nullptr;
+        srcb[f] = f < S ? tdl::opaque(reinterpret_cast<const T*>(p.src[f]) + (size_t)b * hw * C) : nullptr;
     const int nchunk = (C + 63) / 64;
     const int cl = 4 * l16;
     const unsigned uC = (unsigned)C;
@@ -524,13 +519,13 @@ __global__ void __launch_bounds__(f2::NT) feat_gather_nhwc_kernel(const FeatDev 
     }
     __syncwarp();
     const bool from_dtgt = p.d_tgt != nullptr;               // g = -d_tgt
-    const T* Gb = opaque(reinterpret_cast<const T*>(from_dtgt ? p.d_tgt : p.G) + (size_t)b * hw * C);
+    const T* Gb = tdl::opaque(reinterpret_cast<const T*>(from_dtgt ? p.d_tgt : p.G) + (size_t)b * hw * C);
     const float sgn = from_dtgt ? -1.f : 1.f;
     float* dsf = p.d_src[0];
 #pragma unroll
     for (int k = 1; k < TDL_MAX_SRC; ++k)
         if (k == f) dsf = p.d_src[k];
-    T* dst = opaque(reinterpret_cast<T*>(dsf) + (size_t)b * hw * C);
+    T* dst = tdl::opaque(reinterpret_cast<T*>(dsf) + (size_t)b * hw * C);
     for (int q = 0; q < PIX; q += 2) {
         const int pl = q + half;
         const int o = o0 + pl;

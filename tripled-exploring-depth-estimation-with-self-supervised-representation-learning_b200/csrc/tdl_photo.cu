@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256, 1) photo_warp_kernel(const PhotoDev p) {
                 const Proj pr = project<false>(g, s_cam + f * 12, pcst);
                 bt[f] = bilin_taps(pr.ix, pr.iy, H, W);
                 // block-uniform 64-bit base + 32-bit per-thread offsets: one integer add per access
-                const float* sb = p.src[f] + (size_t)b * 3 * HW;
+                const float* sb = opaque(p.src[f] + (size_t)b * 3 * HW);
                 const unsigned o00 = (unsigned)(bt[f].y0 * W + bt[f].x0);
                 const unsigned o01 = o00 + (bt[f].vx ? 1u : 0u), o10 = o00 + (bt[f].vy ? (unsigned)W : 0u);
                 const unsigned o11 = o10 + (bt[f].vx ? 1u : 0u);
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(256, 1) photo_warp_kernel(const PhotoDev p) {
             }
 #pragma unroll
             for (int f = 0; f < S; ++f) {
-                float* wo = p.warped[s][f] + (size_t)b * 3 * HW;
+                float* wo = opaque(p.warped[s][f] + (size_t)b * 3 * HW);
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     float acc = v[f][ch][0] * bt[f].nw;
@@ -1098,7 +1098,7 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
 #pragma unroll
         for (int k = 0; k < 12; ++k) aP[k] = 0.f;
         const float* Pf = s_cam + f * 12;
-        const float* sbase = p.src[f] + (size_t)b * 3 * HW;
+        const float* sbase = opaque(p.src[f] + (size_t)b * 3 * HW);     // (+ 32-bit tap offsets: one multiply-add per address)
 #pragma unroll
         for (int i0 = 0; i0 < kR; i0 += 2) {
             bool act[2];
@@ -1114,14 +1114,16 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const float* q = sbase + (size_t)bt[u].y0 * W + bt[u].x0;
-                const int dx = bt[u].vx ? 1 : 0, dy = bt[u].vy ? W : 0;
+                const unsigned o00 = (unsigned)(bt[u].y0 * W + bt[u].x0);
+                const unsigned o01 = o00 + (bt[u].vx ? 1u : 0u), o10 = o00 + (bt[u].vy ? (unsigned)W : 0u);
+                const unsigned o11 = o10 + (bt[u].vx ? 1u : 0u);
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    v[u][ch][0] = act[u] ? __ldg(q + ch * HW) : 0.f;
-                    v[u][ch][1] = act[u] ? __ldg(q + ch * HW + dx) : 0.f;
-                    v[u][ch][2] = act[u] ? __ldg(q + ch * HW + dy) : 0.f;
-                    v[u][ch][3] = act[u] ? __ldg(q + ch * HW + dy + dx) : 0.f;
+                    const unsigned co = (unsigned)ch * (unsigned)HW;
+                    v[u][ch][0] = act[u] ? __ldg(sbase + (co + o00)) : 0.f;
+                    v[u][ch][1] = act[u] ? __ldg(sbase + (co + o01)) : 0.f;
+                    v[u][ch][2] = act[u] ? __ldg(sbase + (co + o10)) : 0.f;
+                    v[u][ch][3] = act[u] ? __ldg(sbase + (co + o11)) : 0.f;
                 }
             }
 #pragma unroll

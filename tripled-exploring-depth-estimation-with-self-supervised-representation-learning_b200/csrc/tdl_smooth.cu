@@ -75,8 +75,8 @@ TDL_DEV Stencil6 edge_weights(const float* __restrict__ Jb, int j, int i, int h,
     const size_t hw = (size_t)h * w;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        const float* pl = Jb + ch * hw;
-        const Stencil6 s = stencils([&](int jj, int ii) { return __ldg(pl + (size_t)jj * w + ii); }, j, i, h, w);
+        const float* pl = opaque(Jb + ch * hw);             // (32-bit pixel offsets on an opaque plane base: see tdl_common.cuh)
+        const Stencil6 s = stencils([&](int jj, int ii) { return __ldg(pl + (unsigned)(jj * w + ii)); }, j, i, h, w);
 #pragma unroll
         for (int k = 0; k < 6; ++k) m.v[k] += fabsf(s.v[k]);
     }
@@ -109,10 +109,10 @@ __global__ void __launch_bounds__(kSmoothNT) smooth_fwd_kernel(const SmoothDev p
         const Counts cn = inv_counts(p.B, C, h, w);
         const float den = L.norm ? norm_denominator(L, b) : 1.f;
         for (int c = 0; c < C; ++c) {
-            const float* pl = L.x + ((size_t)b * C + c) * h * w;
+            const float* pl = opaque(L.x + ((size_t)b * C + c) * h * w);
             const Stencil6 s = stencils(
                 [&](int jj, int ii) {
-                    const float v = __ldg(pl + (size_t)jj * w + ii);
+                    const float v = __ldg(pl + (unsigned)(jj * w + ii));
                     return L.norm ? div_rn(v, den) : v;
                 },
                 j, i, h, w);
@@ -160,13 +160,14 @@ __global__ void __launch_bounds__(kSmoothNT) smooth_bwd_kernel(const SmoothDev p
                             {0.f, 0.f, 0.f, 0.f, 0.f, 1.f},        // anchor (-2,0)
                             {0.f, 0.f, 0.f, 1.f, 1.f, 0.f}};       // anchor (-1,-1)
     Stencil6 wt[6];
+    const float* wtb = opaque(L.Wt + (size_t)b * 6 * h * w);
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
         const int jj = j + aj[a], ii = i + ai[a];
         if (jj >= 0 && ii >= 0) {
 #pragma unroll
             for (int k = 0; k < 6; ++k)
-                wt[a].v[k] = (cf[a][k] != 0.f) ? __ldg(L.Wt + ((size_t)b * 6 + k) * h * w + (size_t)jj * w + ii) : 0.f;
+                wt[a].v[k] = (cf[a][k] != 0.f) ? __ldg(wtb + (unsigned)(k * h * w + jj * w + ii)) : 0.f;
         } else {
 #pragma unroll
             for (int k = 0; k < 6; ++k) wt[a].v[k] = 0.f;
@@ -180,9 +181,9 @@ __global__ void __launch_bounds__(kSmoothNT) smooth_bwd_kernel(const SmoothDev p
         euler = up * (float)(Lb / ((double)h * (double)w));
     }
     for (int c = 0; c < C; ++c) {
-        const float* pl = L.x + ((size_t)b * C + c) * h * w;
+        const float* pl = opaque(L.x + ((size_t)b * C + c) * h * w);
         auto ld = [&](int jj, int ii) {
-            const float v = __ldg(pl + (size_t)jj * w + ii);
+            const float v = __ldg(pl + (unsigned)(jj * w + ii));
             return L.norm ? div_rn(v, den) : v;
         };
         float g = 0.f;
