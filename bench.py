@@ -321,10 +321,18 @@ def measure_workload(frames, args, device, rank, world, dist_on, trainable, feat
         step.run_eager()
     torch.cuda.synchronize(device)
     prof_steps = min(args.steps, 20)
+    # per-kernel times: eager steps on ONE stream (with the two-stream schedule a kernel's event pair also measures the
+    # time it waits for the other stream's CTAs to drain, which is not its own duration)
+    step.net.overlap_streams = False
+    step.run_eager()
+    torch.cuda.synchronize(device)
     tdl._lib.profile_begin()
     for _ in range(prof_steps):
         step.run_eager()
     kern = tdl._lib.profile_end()
+    step.net.overlap_streams = True
+    step.run_eager()
+    torch.cuda.synchronize(device)
     ident = step.identity_frac()
     launches_per_step = sum(n for k, (n, _) in kern.items() if not k.startswith("memset")) // prof_steps
     step.capture()

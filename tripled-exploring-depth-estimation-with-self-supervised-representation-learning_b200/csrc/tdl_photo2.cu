@@ -343,7 +343,11 @@ __global__ void __launch_bounds__(s2::NT, S <= 2 ? 3 : 2) photo_score2_kernel(co
         // ---- work list of the backward (photo_bwd_list_kernel): every window whose arg-min is a warped frame is appended
         //      to the list of its (scale, image) as pixel | frame << 28; one atomic per warp reserves the slots.  The count
         //      keeps running past the capacity (the backward then knows the list is incomplete and runs the tile kernel).
-        if (p.list_max >= 0) {
+        // (a list that already overflowed is closed: its count only has to stay above the capacity, so the warps of a
+        //  densely selected image skip the scan, the atomic and the stores -- the count is read past L1, one lane decides)
+        bool list_open = p.list_max >= 0;
+        if (list_open) list_open = __shfl_sync(0xffffffffu, __ldcg(p.lcnt + s * p.B + b) <= kListCap ? 1 : 0, 0) != 0;
+        if (list_open) {
             int cnt = 0;
 #pragma unroll
             for (int i = 0; i < kPP; ++i) cnt += (arg[i] >= chan0 && gy0 + i / kPC < H && gx0 < W) ? 1 : 0;
