@@ -718,9 +718,10 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
     __shared__ float s_dP[TDL_MAX_SRC * 12];
     __shared__ int s_cnt[TDL_MAX_SRC];
-    __shared__ int s_nall;              // selected windows of the tile (all frames)
     __shared__ int s_nlive;             // sparse path: live (frame, pixel) pairs (its own counter: zeroed before the first barrier)
-    __shared__ unsigned short s_list[PH * PW + 128];   // selected windows (<= PH*PW); sparse path: 128 windows + 9*128 live pairs
+    constexpr int kLCAP = PH * PW;                       // capacity of one frame's window list
+    __shared__ unsigned short s_list[S * kLCAP];         // selected windows (cell index), one list per frame
+    __shared__ unsigned short s_live[9 * 128];           // sparse path: live (pixel | frame << 11) pairs of <= 128 windows
     __shared__ int s_tx0[kTW], s_tx1[kTW], s_ty0[kTH], s_ty1[kTH];
     __shared__ float s_tlx[kTW], s_tly[kTH];
 
@@ -751,8 +752,14 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
         s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
         s_dP[tid] = 0.f;
     }
+    // the coefficient planes start from zero (16-byte stores, issued while the TMA copies fly): the dense path then only
+    // ever clears the windows of the frame it has finished, and the sparse path finds its accumulators / bit map cleared
+    {
+        float4* z = reinterpret_cast<float4*>(s_coef);
+        for (int i = tid; i < 9 * QPLANE / 4; i += kNT) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        static_assert((9 * QPLANE) % 4 == 0 && QGROUP % 4 == 0, "16-byte stores over the coefficient planes");
+    }
     if (tid >= 128 && tid < 128 + TDL_MAX_SRC) s_cnt[tid - 128] = 0;
-    if (tid == 255) s_nall = 0;
     if (tid == 254) s_nlive = 0;
     if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
     const float* s_iK = s_cam + TDL_MAX_SRC * 12;
@@ -882,19 +889,21 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
     const float g_ssim = up * 0.85f / 3.f, g_l1 = up * 0.15f / 3.f;
 
     // ---- phase 2a: the windows (tile + halo 1) whose arg-min is a WARPED frame carry gradient; they are compacted into
-    //      one list (window cell | frame << 11) so that the heavy statistics run with full warps.
+    //      ONE LIST PER FRAME (window cell; frame k's list starts at k * kLCAP), so that the heavy statistics run with
+    //      full warps: a warp of the per-frame loop below then holds 32 windows of the same frame (one mixed list left
+    //      half of the lanes idle in each of the S passes wherever the frames mix at pixel level -- the rule on a moving
+    //      scene: 236 M -> 207 M warp-instructions on the bench's scene workload).
     const int chan0 = p.automask ? S : 0;
     for (int i = tid; i < PH * PW; i += kNT) {
         const int r = i / PW, c = i - r * PW;
         const int q = (r + 1) * QW + c + kQX0 - 1;
         const int f = (int)s_mask[q] - chan0;
-        if (f >= 0 && f < S) {
-            atomicAdd(&s_cnt[f], 1);
-            s_list[atomicAdd(&s_nall, 1)] = (unsigned short)(q | (f << 11));
-        }
+        if (f >= 0 && f < S) s_list[f * kLCAP + atomicAdd(&s_cnt[f], 1)] = (unsigned short)q;
     }
     __syncthreads();
-    const int n_all = s_nall;
+    int n_all = 0;
+#pragma unroll
+    for (int k = 0; k < S; ++k) n_all += s_cnt[k];
     if (n_all == 0) return;                       // automasking: nothing selected in this tile (CTA-uniform)
 
     if (n_all <= p.sparse_max) {
@@ -905,13 +914,17 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
         constexpr int TP = kTH * kTW;
         float* s_G = s_coef;                                  // [S][3][TP]
         unsigned* s_bits = reinterpret_cast<unsigned*>(s_coef + S * 3 * TP);   // [S][TP / 32]: pixel already in the live list
-        for (int i = tid; i < S * 3 * TP; i += kNT) s_G[i] = 0.f;
-        if (tid < S * TP / 32) s_bits[tid] = 0u;
-        __syncthreads();
-        unsigned short* s_live = s_list + 128;                // <= 9 * n_all <= 1152 entries, behind the <= 128 windows
+        static_assert(S * 3 * TP + S * TP / 32 <= 9 * QPLANE, "accumulators + bit map inside the (pre-zeroed) coefficient planes");
         for (int e = tid; e < 3 * n_all; e += kNT) {          // one thread per (selected window, channel)
-            const int ent = s_list[e / 3], ch = e - (e / 3) * 3;
-            const int q = ent & 2047, f = ent >> 11;
+            int wi = e / 3, f = 0;
+            const int ch = e - wi * 3;
+#pragma unroll
+            for (int k = 0; k < S - 1; ++k)
+                if (f == k && wi >= s_cnt[k]) {
+                    wi -= s_cnt[k];
+                    f = k + 1;
+                }
+            const int q = s_list[f * kLCAP + wi];
             const int r = q / QW, c = q - r * QW;
             const int wy = ty0 - kQY0 + r, wx = tx0 - kQX0 + c;           // image coordinates of the window centre
             const float* xs = s_wrp + f * QGROUP + ch * QPLANE + q;
@@ -1014,23 +1027,28 @@ __global__ void __launch_bounds__(kNT, 2) photo_bwd_kernel(const PhotoDev p, con
 #pragma unroll
     for (int i = 0; i < kR; ++i) geo[i] = backproject(dval[i], dp, s_iK, gx, ty0 + r0 + i);
 
+    int prev_f = -1;
 #pragma unroll 1
     for (int f = 0; f < S; ++f) {
         const int chan = chan0 + f;
-        if (s_cnt[f] == 0) continue;              // CTA-uniform
-        // ---- phase 2b: SSIM adjoint coefficients of every window centre; the unselected windows store zeros
-        for (int i = tid; i < PH * PW; i += kNT) {
-            const int r = i / PW, c = i - r * PW;
-            const int q = (r + 1) * QW + c + kQX0 - 1;
-            if (s_mask[q] != chan) {
+        const int n_f = s_cnt[f];                 // windows that selected this frame
+        if (n_f == 0) continue;                   // CTA-uniform
+        const unsigned short* lst = s_list + f * kLCAP;
+        // ---- phase 2b: SSIM adjoint coefficients of the windows that selected this frame; every other cell of the planes
+        //      is zero: they start zeroed and the windows of the previous frame (other cells than this frame's: a window
+        //      selects one frame) are cleared here through that frame's list
+        if (prev_f >= 0) {                        // CTA-uniform
+            const unsigned short* pl = s_list + prev_f * kLCAP;
+            const int n_p = s_cnt[prev_f];
+            for (int e = tid; e < n_p; e += kNT) {
+                const int q = pl[e];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) s_coef[k * QPLANE + q] = 0.f;
             }
         }
-        for (int e = tid; e < n_all; e += kNT) {
-            const int ent = s_list[e];
-            if ((ent >> 11) != f) continue;
-            const int q = ent & 2047;
+        prev_f = f;
+        for (int e = tid; e < n_f; e += kNT) {
+            const int q = lst[e];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 float cA, cB, cC;
