@@ -33,6 +33,9 @@
  *   tdl_pose_fwd / tdl_pose_bwd
  *       transformation_from_parameters  mono/model/mono_fm/net.py:201-212 (get_translation_matrix :214-222,
  *                                       rot_from_axisangle :224-253), called by predict_poses (net.py:142-155)
+ *   tdl_input_fwd  (the per-item host work of the data loader, on uint8 frames already resident on the device)
+ *       to_tensor + color_aug           mono/datasets/mono_dataset.py:84-103 (ColorJitter ranges :62-73, sampled :182-187)
+ *       erase masks                     mono/datasets/kitti_dataset.py:167-182 (cfg erase_count / erase_shape)
  *
  * Conventions
  *   - every tensor is fp32, NCHW, contiguous, resident in device memory; only
@@ -54,7 +57,7 @@
 extern "C" {
 #endif
 
-#define TDL_ABI_VERSION 3
+#define TDL_ABI_VERSION 4
 #define TDL_MAX_SRC 4      /* source frames per target (frame_ids[1:])       */
 #define TDL_MAX_SCALES 4   /* disparity scales (opt.scales)                  */
 #define TDL_MAX_LEVELS 5   /* encoder levels of get_feature_regularization_loss */
@@ -237,6 +240,31 @@ typedef struct tdl_proj_args {
     float* dT[TDL_MAX_SRC];              /* out (B,4,4) per frame, overwritten; NULL entries are skipped  */
 } tdl_proj_args;
 
+/* ------------------------------------------------------------------ input pipeline (uint8 frames -> color, color_aug, mask) */
+/* Byte-exact torchvision ColorJitter on PIL images (Pillow's Image.blend / convert("L") / convert("HSV") arithmetic),
+ * transforms.ToTensor and the inpainting erase mask, for a whole batch in two launches.  The caller samples the
+ * augmentation parameters the way torchvision's ColorJitter.get_params does (host side, a few numbers per image). */
+typedef struct tdl_input_args {
+    int32_t B, H, W;
+    int32_t nframes;            /* frames per item (target + sources), 1..TDL_MAX_SRC+1                       */
+    int32_t erase_count;        /* boxes per image (cfg.erase_count); 0 = no mask                              */
+    int32_t erase_h, erase_w;   /* cfg.erase_shape                                                             */
+    int32_t reserved0;
+    const uint8_t* frames[TDL_MAX_SRC + 1];  /* (B,H,W,3) uint8, the resized PIL frames' memory layout         */
+    const float* jitter;        /* (B,nframes,4): brightness, contrast, saturation factors and the BYTE added to the hue
+                                   channel, float(uint8(int32(hue_factor * 255))); NULL => color_aug = color    */
+    const int32_t* order;       /* (B,nframes,4): ColorJitter's fn_idx permutation (0 brightness, 1 contrast,
+                                   2 saturation, 3 hue); entries outside 0..3 skip the step                     */
+    const uint8_t* do_aug;      /* (B): do_color_aug of the item; required when jitter != NULL                  */
+    const uint8_t* do_flip;     /* (B) or NULL: horizontal flip of the item's frames                            */
+    const int32_t* holes;       /* (B,erase_count,2): (row, col) of each box's top-left corner                  */
+    float* color[TDL_MAX_SRC + 1];      /* out, optional (B,3,H,W): inputs[("color", f, 0)]                    */
+    float* color_aug[TDL_MAX_SRC + 1];  /* out, optional (B,3,H,W): inputs[("color_aug", f, 0)]                */
+    float* mask;                /* out, optional (B,3,H,W) of 0 / 1: inputs[("mask", 0, 0)]                     */
+    void* workspace;            /* >= tdl_input_ws_bytes(B, nframes) when jitter != NULL                        */
+    uint64_t workspace_bytes;
+} tdl_input_args;
+
 int tdl_abi_version(void);
 const char* tdl_strerror(int code);
 /* Process-wide switches for tests and kernel experiments (the defaults are the product path).  They are
@@ -281,6 +309,9 @@ int tdl_pose_bwd(const tdl_pose_args* args, tdl_stream_t stream);
 
 int tdl_proj_fwd(const tdl_proj_args* args, tdl_stream_t stream);
 int tdl_proj_bwd(const tdl_proj_args* args, tdl_stream_t stream);
+
+uint64_t tdl_input_ws_bytes(int32_t B, int32_t nframes);
+int tdl_input_fwd(const tdl_input_args* args, tdl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol(lib, tdl):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/tdl.h but not exported by libtdl.so"
     assert sorted(tdl._lib.EXPORTS) == names
-    assert lib.tdl_abi_version() == tdl._lib.TDL_ABI_VERSION == 3
+    assert lib.tdl_abi_version() == tdl._lib.TDL_ABI_VERSION == 4
     assert lib.tdl_strerror(0) == b"ok"
     assert b"NULL" in lib.tdl_strerror(-1)
 
@@ -51,6 +51,8 @@ int main(void) {
   printf("%zu %zu %zu\\n", sizeof(tdl_recon_args), offsetof(tdl_recon_args, pred), offsetof(tdl_recon_args, d_pred));
   printf("%zu %zu %zu %zu\\n", sizeof(tdl_pose_args), offsetof(tdl_pose_args, axisangle), offsetof(tdl_pose_args, dT),
          offsetof(tdl_feat_args, bwd_scratch));
+  printf("%zu %zu %zu %zu %zu\\n", sizeof(tdl_input_args), offsetof(tdl_input_args, frames), offsetof(tdl_input_args, jitter),
+         offsetof(tdl_input_args, color_aug), offsetof(tdl_input_args, workspace_bytes));
   return 0; }''')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
@@ -69,6 +71,9 @@ int main(void) {
     assert list(map(int, out[4].split())) == [C.sizeof(Rc), Rc.pred.offset, Rc.d_pred.offset]
     Po = L.PoseArgs
     assert list(map(int, out[5].split())) == [C.sizeof(Po), Po.axisangle.offset, Po.dT.offset, F.bwd_scratch.offset]
+    In = L.InputArgs
+    assert list(map(int, out[6].split())) == [C.sizeof(In), In.frames.offset, In.jitter.offset, In.color_aug.offset,
+                                              In.workspace_bytes.offset]
 
 
 def test_argument_errors_without_a_gpu(lib, tdl):
@@ -102,6 +107,17 @@ def test_argument_errors_without_a_gpu(lib, tdl):
     pa.B, pa.axisangle, pa.translation, pa.T = 0, p, p, p
     assert lib.tdl_pose_fwd(C.byref(pa), None) == -2                 # TDL_ERR_SHAPE
     assert lib.tdl_launch_count(b"tdl_photo_fwd") == 4
+    assert lib.tdl_input_fwd(None, None) == -1
+    ia = L.InputArgs()
+    ia.B, ia.H, ia.W, ia.nframes = 1, 8, 8, 6
+    assert lib.tdl_input_fwd(C.byref(ia), None) == -4                # TDL_ERR_COUNT (nframes > TDL_MAX_SRC + 1)
+    ia.nframes = 1
+    assert lib.tdl_input_fwd(C.byref(ia), None) == -1                # frames[0] missing
+    ia.frames[0] = p
+    ia.jitter = ia.order = ia.do_aug = ia.workspace = p
+    ia.workspace_bytes = 4
+    assert lib.tdl_input_fwd(C.byref(ia), None) == -3                # TDL_ERR_WORKSPACE
+    assert lib.tdl_input_ws_bytes(8, 3) >= 8 * 3 * 8
     # valid arguments but no sm_100 device behind the call: TDL_ERR_NODEVICE, never a raw cudaError / a launch
     import torch
     if not torch.cuda.is_available():

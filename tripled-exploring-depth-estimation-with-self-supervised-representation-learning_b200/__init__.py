@@ -5,7 +5,8 @@ bound with ctypes (``_lib``), wrapped as autograd Functions (``ops``) and expose
 reference's ``compute_losses`` / ``generate_images_pred`` / ``generate_features_pred`` methods
 (``losses``, ``nets``).  See DESIGN.md.
 """
-from . import _lib, config, geometry, losses, ops, registry, synth  # noqa: F401
+from . import _lib, config, geometry, input_pipeline, losses, ops, registry, synth  # noqa: F401
 from .config import Config  # noqa: F401
+from .input_pipeline import GpuInputPipeline  # noqa: F401
 from .losses import ViewSynthesisLossMixin  # noqa: F401
 from .registry import MONO  # noqa: F401

@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("TDL_LIB_PATH") or os.path.join(HERE, "libtdl.so")   #
 
 TDL_MAX_SRC = 4
 TDL_MAX_SCALES = 4
-TDL_ABI_VERSION = 3
+TDL_ABI_VERSION = 4
 TDL_LAYOUT_NCHW, TDL_LAYOUT_NHWC = 0, 1
 TDL_DTYPE_F32, TDL_DTYPE_BF16 = 0, 1
 
@@ -97,6 +97,17 @@ class ProjArgs(C.Structure):
     ]
 
 
+class InputArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("nframes", C.c_int32),
+        ("erase_count", C.c_int32), ("erase_h", C.c_int32), ("erase_w", C.c_int32), ("reserved0", C.c_int32),
+        ("frames", _vp * (TDL_MAX_SRC + 1)),
+        ("jitter", _vp), ("order", _vp), ("do_aug", _vp), ("do_flip", _vp), ("holes", _vp),
+        ("color", _vp * (TDL_MAX_SRC + 1)), ("color_aug", _vp * (TDL_MAX_SRC + 1)), ("mask", _vp),
+        ("workspace", _vp), ("workspace_bytes", C.c_uint64),
+    ]
+
+
 class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int32), ("total_ms", C.c_double)]
 
@@ -106,7 +117,7 @@ EXPORTS = ["tdl_abi_version", "tdl_strerror", "tdl_set_option", "tdl_get_option"
            "tdl_feat_ws_bytes", "tdl_feat_bwd_scratch_bytes", "tdl_feat_fwd", "tdl_feat_bwd",
            "tdl_edge_ws_bytes", "tdl_edge_smooth_fwd", "tdl_edge_smooth_bwd", "tdl_edge_smooth_multi_fwd", "tdl_edge_smooth_multi_bwd",
            "tdl_recon_ws_bytes", "tdl_recon_fwd", "tdl_recon_bwd", "tdl_pose_fwd", "tdl_pose_bwd",
-           "tdl_proj_fwd", "tdl_proj_bwd"]
+           "tdl_proj_fwd", "tdl_proj_bwd", "tdl_input_ws_bytes", "tdl_input_fwd"]
 
 _lib = None
 
@@ -144,6 +155,8 @@ def lib():
     L.tdl_feat_bwd_scratch_bytes.argtypes = [C.c_int32] * 5
     L.tdl_recon_ws_bytes.restype = C.c_uint64
     L.tdl_recon_ws_bytes.argtypes = []
+    L.tdl_input_ws_bytes.restype = C.c_uint64
+    L.tdl_input_ws_bytes.argtypes = [C.c_int32] * 2
     L.tdl_edge_ws_bytes.restype = C.c_uint64
     L.tdl_edge_ws_bytes.argtypes = [C.c_int32] * 4
     for name, T in (("tdl_photo_fwd", PhotoArgs), ("tdl_photo_bwd", PhotoArgs),
@@ -152,7 +165,7 @@ def lib():
                     ("tdl_edge_smooth_multi_fwd", EdgeMultiArgs), ("tdl_edge_smooth_multi_bwd", EdgeMultiArgs),
                     ("tdl_recon_fwd", ReconArgs), ("tdl_recon_bwd", ReconArgs),
                     ("tdl_pose_fwd", PoseArgs), ("tdl_pose_bwd", PoseArgs),
-                    ("tdl_proj_fwd", ProjArgs), ("tdl_proj_bwd", ProjArgs)):
+                    ("tdl_proj_fwd", ProjArgs), ("tdl_proj_bwd", ProjArgs), ("tdl_input_fwd", InputArgs)):
         fn = getattr(L, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(T), C.c_void_p]

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libtdl.so")
-SOURCES = ["tdl_api.cu", "tdl_photo.cu", "tdl_photo2.cu", "tdl_smooth.cu", "tdl_feat.cu", "tdl_feat2.cu", "tdl_pose.cu"]
+SOURCES = ["tdl_api.cu", "tdl_photo.cu", "tdl_photo2.cu", "tdl_smooth.cu", "tdl_feat.cu", "tdl_feat2.cu", "tdl_pose.cu", "tdl_input.cu"]
 HEADERS = [os.path.join(CSRC, "tdl_common.cuh"), os.path.join(CSRC, "tdl_ssim.cuh"), os.path.join(CSRC, "tdl_internal.h"), os.path.join(CSRC, "tdl_tma.cuh"),
            os.path.join(ROOT, "include", "tdl.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -293,6 +293,7 @@ int tdl_launch_count(const char* entry) {
     if (!strcmp(entry, "tdl_recon_bwd")) return 1;
     if (!strcmp(entry, "tdl_pose_fwd") || !strcmp(entry, "tdl_pose_bwd")) return 1;
     if (!strcmp(entry, "tdl_proj_fwd") || !strcmp(entry, "tdl_proj_bwd")) return 1;
+    if (!strcmp(entry, "tdl_input_fwd")) return 2;        // input_stat (with jitter), input_apply
     return 0;
 }
 
@@ -715,6 +716,43 @@ int tdl_proj_bwd(const tdl_proj_args* a, tdl_stream_t stream) {
     if (const int rc = check_device()) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TDL_KERNEL("proj_bwd", launch_proj_bwd(*a, st));
+    return TDL_OK;
+}
+
+// ------------------------------------------------------------------------------------ input pipeline
+uint64_t tdl_input_ws_bytes(int32_t B, int32_t nframes) {
+    if (B < 1 || nframes < 1) return 0;
+    return align_up((uint64_t)B * nframes * sizeof(unsigned long long), 256);
+}
+
+int tdl_input_fwd(const tdl_input_args* a, tdl_stream_t stream) {
+    if (!a) return TDL_ERR_NULL;
+    if (a->nframes < 1 || a->nframes > TDL_MAX_SRC + 1) return TDL_ERR_COUNT;
+    if (a->B < 1 || a->H < 1 || a->W < 1 || (int64_t)a->H * a->W > (int64_t)1 << 30) return TDL_ERR_SHAPE;
+    if (a->erase_count < 0 || (a->erase_count > 0 && (a->erase_h < 1 || a->erase_w < 1))) return TDL_ERR_SHAPE;
+    for (int f = 0; f < a->nframes; ++f)
+        if (!a->frames[f]) return TDL_ERR_NULL;
+    if (a->jitter && (!a->order || !a->do_aug || !a->workspace)) return TDL_ERR_NULL;
+    if (a->mask && a->erase_count > 0 && !a->holes) return TDL_ERR_NULL;
+    if (a->jitter && a->workspace_bytes < tdl_input_ws_bytes(a->B, a->nframes)) return TDL_ERR_WORKSPACE;
+    if (const int rc = check_device()) return rc;
+    InputDev d{};
+    d.B = a->B; d.H = a->H; d.W = a->W; d.nframes = a->nframes;
+    d.erase_count = a->mask ? a->erase_count : 0; d.erase_h = a->erase_h; d.erase_w = a->erase_w;
+    for (int f = 0; f < a->nframes; ++f) {
+        d.frames[f] = a->frames[f];
+        d.color[f] = a->color[f];
+        d.color_aug[f] = a->color_aug[f];
+    }
+    d.jitter = a->jitter; d.order = a->order; d.do_aug = a->do_aug; d.do_flip = a->do_flip; d.holes = a->holes;
+    d.mask = a->mask;
+    d.gsum = static_cast<unsigned long long*>(a->workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d.jitter) {
+        TDL_KERNEL("memset", cudaMemsetAsync(d.gsum, 0, (size_t)d.B * d.nframes * sizeof(unsigned long long), st));
+        TDL_KERNEL("input_stat", launch_input_stat(d, st));
+    }
+    TDL_KERNEL("input_apply", launch_input_apply(d, st));
     return TDL_OK;
 }
 

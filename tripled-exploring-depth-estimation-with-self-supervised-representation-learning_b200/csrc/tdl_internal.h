@@ -175,6 +175,23 @@ cudaError_t launch_feat_overflow_nhwc(const FeatDev& p, cudaStream_t st);
 cudaError_t launch_edge_finalize(const double* acc, int acc_stride, int B, float first_coef, float second_coef,
                                  int h, int w, float* loss, cudaStream_t st);
 
+// input pipeline (tdl_input.cu)
+struct InputDev {
+    int B, H, W, nframes, erase_count, erase_h, erase_w;
+    const unsigned char* frames[TDL_MAX_SRC + 1];
+    const float* jitter;
+    const int* order;
+    const unsigned char* do_aug;
+    const unsigned char* do_flip;
+    const int* holes;
+    float* color[TDL_MAX_SRC + 1];
+    float* color_aug[TDL_MAX_SRC + 1];
+    float* mask;
+    unsigned long long* gsum;    // [B][nframes] grey sums for ImageEnhance.Contrast
+};
+cudaError_t launch_input_stat(const InputDev& p, cudaStream_t st);
+cudaError_t launch_input_apply(const InputDev& p, cudaStream_t st);
+
 cudaError_t launch_proj_fwd(const tdl_proj_args& a, cudaStream_t st);
 cudaError_t launch_proj_bwd(const tdl_proj_args& a, cudaStream_t st);
 cudaError_t launch_pose_fwd(const float* aa, const float* tr, int B, int invert, float* T, cudaStream_t st);
