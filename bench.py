@@ -387,8 +387,14 @@ class ImagesOnlyStep(DeviceStep):
     def __init__(self, host, B, H, W, device, trainable_feat=True):
         keep = {k: v for k, v in host.items() if not (k[0] == "leaf" and (k[1] == "tgt_feat" or (isinstance(k[1], tuple) and k[1][0] == "src_feat")))}
         super().__init__(keep, B, H, W, device, True)
-        self.frames_u8 = {f: (host[("in", ("color", f, 0))] * 255).round().to(torch.uint8).pin_memory() for f in FRAME_IDS}
+        # what a decoder / PIL resize hands over: (B,H,W,3) uint8; the on-GPU input pipeline (tdl_input_fwd) turns them into
+        # inputs[("color", f, 0)] and inputs[("color_aug", f, 0)] (torchvision ColorJitter, byte-exact) every step
+        self.frames_u8 = {f: (host[("in", ("color", f, 0))] * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory()
+                          for f in FRAME_IDS}
         self.frames_dev = {f: torch.empty_like(v, device=device) for f, v in self.frames_u8.items()}
+        self.pipe = self.tdl.GpuInputPipeline(FRAME_IDS, H, W)
+        self.params = {k: (v.to(device) if v is not None else None)
+                       for k, v in self.pipe.sample_params(B, torch.Generator().manual_seed(5)).items()}
         self.host = {k: v for k, v in self.host.items() if k[0] == "in" and not isinstance(k[1], tuple)}   # K, inv_K
         g = torch.Generator().manual_seed(0)
         self.stem = (torch.randn(FEAT_C, 3, 7, 7, generator=g) * 0.1).to(device)
@@ -401,8 +407,11 @@ class ImagesOnlyStep(DeviceStep):
         for k in self.grad_keys:
             b[k].grad = None
         self.stem.grad = None
-        imgs = {f: self.frames_dev[f].float() * (1.0 / 255.0) for f in FRAME_IDS}
-        conv_in = {f: (v.contiguous(memory_format=torch.channels_last) if FEAT_LAYOUT == "nhwc" else v) for f, v in imgs.items()}
+        pre = self.pipe(self.frames_dev, self.params)
+        imgs = {f: pre[("color", f, 0)] for f in FRAME_IDS}
+        # the networks see the augmented frames, the loss the plain ones (mono/model/mono_fm/net.py:41-46)
+        conv_in = {f: (pre[("color_aug", f, 0)].contiguous(memory_format=torch.channels_last) if FEAT_LAYOUT == "nhwc"
+                       else pre[("color_aug", f, 0)]) for f in FRAME_IDS}
         inputs = {k[1]: v for k, v in b.items() if k[0] == "in" and not isinstance(k[1], tuple)}
         for f in FRAME_IDS:
             inputs[("color", f, 0)] = imgs[f]
@@ -427,6 +436,69 @@ class ImagesOnlyStep(DeviceStep):
 
     def h2d_bytes(self):
         return sum(v.numel() for v in self.frames_u8.values()) + sum(v.numel() * v.element_size() for v in self.host.values())
+
+
+def input_pipeline_bench(B, H, W, device, steps, cpu_baseline=True):
+    """The on-GPU input pipeline on the TripleD item shape: 3 frames, colour jitter on every image,
+    16 erase boxes of 16x16 (cfg_kitti_tripleD.py:19-20).  Device time by CUDA events over `steps` calls; the CPU figure
+    is the reference's way -- torchvision ColorJitter on PIL images + ToTensor + the mask, one item after the other."""
+    tdl = importlib.import_module(PKG)
+    g = torch.Generator().manual_seed(77)
+    frames = {f: (torch.rand(B, H, W, 3, generator=g) ** 2 * 255).to(torch.uint8) for f in FRAME_IDS}
+    pipe = tdl.GpuInputPipeline(FRAME_IDS, H, W, erase_count=16, erase_shape=(16, 16))
+    params = pipe.sample_params(B, g)
+    params["do_aug"][:] = 1
+    dev_frames = {f: v.to(device) for f, v in frames.items()}
+    dev_params = {k: (v.to(device) if v is not None else None) for k, v in params.items()}
+    for _ in range(3):
+        pipe(dev_frames, dev_params)
+    torch.cuda.synchronize(device)
+    graph = torch.cuda.CUDAGraph()                       # (device time of the launches, not of the Python call)
+    with torch.cuda.graph(graph, stream=torch.cuda.current_stream(device)):
+        keep = pipe(dev_frames, dev_params)
+    for _ in range(3):
+        graph.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize(device)
+    del keep
+    us = e0.elapsed_time(e1) / steps * 1e3
+    nf, n = len(FRAME_IDS), B * H * W
+    alg = n * nf * (3 + 3 + 24) + n * 12            # statistics pass + apply pass reads, color + color_aug writes, mask
+    out = {"us_per_batch": round(us, 2), "images_per_s": round(B / us * 1e6, 1), "alg_bytes": alg,
+           "gbs": round(alg / us * 1e-3, 1), "launches": 2,
+           "what": f"tdl_input_fwd: {nf} uint8 frames x batch {B} at {H}x{W} -> color, color_aug (ColorJitter on every image), "
+                   "16 erase boxes; bit-exact against torchvision / Pillow (tests/test_input_pipeline.py)"}
+    if cpu_baseline:
+        try:
+            from PIL import Image
+            from torchvision import transforms
+            cj = transforms.ColorJitter((0.8, 1.2), (0.8, 1.2), (0.8, 1.2), (-0.1, 0.1))
+            tt = transforms.ToTensor()
+            imgs = [[Image.fromarray(frames[f][b].numpy()) for f in FRAME_IDS] for b in range(B)]
+            t0 = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                for b in range(B):
+                    for im in imgs[b]:
+                        tt(im)
+                        tt(cj(im))
+                    m = torch.ones(3, H, W, dtype=torch.uint8)
+                    for _c in range(16):
+                        r_ = int(torch.LongTensor(1).random_(0, H - 17)[0])
+                        c_ = int(torch.LongTensor(1).random_(0, W - 17)[0])
+                        m[:, r_:r_ + 16, c_:c_ + 16] = 0
+            dt = (time.perf_counter() - t0) / reps
+            out["cpu_baseline"] = {"images_per_s": round(B / dt, 1), "ms_per_batch": round(dt * 1e3, 1), "cores": 1, "kind": "reference",
+                                   "sample": f"{reps} batches of {B} items: torchvision ColorJitter + ToTensor on PIL images and the "
+                                             "mask loop of kitti_dataset.py:167-182, one DataLoader worker's share (single thread)"}
+        except Exception as exc:                       # pragma: no cover - baseline only
+            out["cpu_baseline"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+    return out
 
 
 def bind_host_near_gpu(local):
@@ -763,6 +835,8 @@ def run():
     io_bytes, io_d2h = io_a.h2d_bytes(), io_a.losses_host.numel() * 4
     del io_a, io_b
 
+    input_pipe = input_pipeline_bench(B, H, W, device, max(args.steps, 10), cpu_baseline=(rank == 0 and not args.no_cpu_baseline))
+
     train = train_tripled = None
     if not args.no_train:
         torch.cuda.empty_cache()
@@ -857,8 +931,10 @@ def run():
                     "steps": e2e_steps},
             "e2e_images_only": {"value": round(io_value, 1), "unit": "images/s", "h2d_bytes_per_step": io_bytes,
                                 "d2h_bytes_per_step": io_d2h, "ms_per_step": round(ms_io / e2e_steps, 4), "steps": e2e_steps,
-                                "what": "uint8 frames + K + inv_K uploaded per step; uint8 -> fp32 conversion, a trainable 7x7/2 conv + "
-                                        "ReLU feature stem (3 frames), loss fwd + bwd through the stem, on the device"},
+                                "what": "uint8 frames + K + inv_K uploaded per step; on-GPU input pipeline (tdl_input_fwd: to_tensor + "
+                                        "ColorJitter), a trainable 7x7/2 conv + ReLU feature stem on the augmented frames (3 frames), "
+                                        "loss fwd + bwd through the stem, on the device"},
+            "input_pipeline": input_pipe,
             "gpu_launches": smooth["launches_per_step"] * args.steps * smooth["repeats"]["n"],
             "gpu_launches_per_step": smooth["launches_per_step"],
             "smooth": block(smooth, k_smooth), "scene": block(scene, dom_tab) if scene else None,

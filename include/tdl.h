@@ -247,7 +247,7 @@ typedef struct tdl_proj_args {
 typedef struct tdl_input_args {
     int32_t B, H, W;
     int32_t nframes;            /* frames per item (target + sources), 1..TDL_MAX_SRC+1                       */
-    int32_t erase_count;        /* boxes per image (cfg.erase_count); 0 = no mask                              */
+    int32_t erase_count;        /* boxes per image (cfg.erase_count), 0..64; 0 = no mask                        */
     int32_t erase_h, erase_w;   /* cfg.erase_shape                                                             */
     int32_t reserved0;
     const uint8_t* frames[TDL_MAX_SRC + 1];  /* (B,H,W,3) uint8, the resized PIL frames' memory layout         */

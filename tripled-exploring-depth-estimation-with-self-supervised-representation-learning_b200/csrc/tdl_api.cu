@@ -730,6 +730,7 @@ int tdl_input_fwd(const tdl_input_args* a, tdl_stream_t stream) {
     if (a->nframes < 1 || a->nframes > TDL_MAX_SRC + 1) return TDL_ERR_COUNT;
     if (a->B < 1 || a->H < 1 || a->W < 1 || (int64_t)a->H * a->W > (int64_t)1 << 30) return TDL_ERR_SHAPE;
     if (a->erase_count < 0 || (a->erase_count > 0 && (a->erase_h < 1 || a->erase_w < 1))) return TDL_ERR_SHAPE;
+    if (a->erase_count > 64) return TDL_ERR_COUNT;
     for (int f = 0; f < a->nframes; ++f)
         if (!a->frames[f]) return TDL_ERR_NULL;
     if (a->jitter && (!a->order || !a->do_aug || !a->workspace)) return TDL_ERR_NULL;

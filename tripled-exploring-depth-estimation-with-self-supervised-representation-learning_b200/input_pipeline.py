@@ -120,6 +120,7 @@ class GpuInputPipeline:
             res[("mask", 0, 0)] = m
             a.mask, a.holes = m.data_ptr(), P["holes"].data_ptr()
         _lib.check(_lib.lib().tdl_input_fwd(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "tdl_input_fwd")
-        for t in keep + [v for v in P.values() if v is not None]:
-            t.record_stream(torch.cuda.current_stream(dev))
+        if not torch.cuda.is_current_stream_capturing():         # (inside a graph everything lives on the capture stream)
+            for t in keep + [v for v in P.values() if v is not None]:
+                t.record_stream(torch.cuda.current_stream(dev))
         return res
