@@ -14,3 +14,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
 ncu --set full --clock-control none --import-source on \
     -k regex:"photo_bwd_kernel|photo_warp_kernel|photo_score2_kernel|feat_fwd_nhwc|feat_bwd_nhwc|feat_gather_nhwc|smooth_fwd_kernel|smooth_bwd_kernel" -s 128 -c 8 \
     -o gpurun_out/${TAG}_full $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "full rc=$?"
+# the two input-pipeline kernels, TripleD item shape
+bash profiles/input_ncu.sh ${TAG}_input

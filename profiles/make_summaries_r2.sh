@@ -33,7 +33,11 @@ REP=gpurun_out/${TAG}_full.ncu-rep
     python profiles/sass_opcount.py $REP $rx 2>/dev/null | head -14; echo '```'
     echo; echo "## \`$rx\`: executed instructions per source line (\`profiles/line_profile.py\`, top 12)"; echo; echo '```'
     python profiles/line_profile.py $REP $rx $TMP/$cub.sm_100a.cubin $mang 12 2>/dev/null | cut -c1-170; echo '```'
-  done; } > profiles/${TAG}_ncu_full_summary.md
+  done
+  if [ -f gpurun_out/${TAG}_input.ncu-rep ]; then
+    echo; echo "## Input pipeline kernels (\`profiles/input_ncu.sh\`: 8 items x 3 frames at 192x640, jitter on every image, 16 erase boxes)"; echo
+    python profiles/ncu_summary.py gpurun_out/${TAG}_input.ncu-rep
+  fi; } > profiles/${TAG}_ncu_full_summary.md
 python - "$REP" "$TAG" <<'PY'
 import csv, json, subprocess, sys
 rep, tag = sys.argv[1], sys.argv[2]
