@@ -168,3 +168,14 @@ def test_full_size_determinism_linearity_and_batch_structure(full_size):
     for k in l1:                                    # permuting the batch leaves the (mean) losses unchanged ...
         assert abs(float(lp[k]) - float(l1[k])) <= 2e-7 * abs(float(l1[k])), k
     assert rel_l2(gp[("disp", 0, 1)].grad, g1[("disp", 0, 1)].grad[perm]) < 2e-5     # ... and permutes the gradients
+
+
+def test_disparity_maps_at_factor_1_and_32_match_oracle():
+    """The decoder's maps sit at H/2 .. H/16; the ABI allows every power of two up to 32 (include/tdl.h).  Full-resolution
+    and H/32 maps exercise the single-pixel and whole-tile cells of the scoring kernel's target pyramid."""
+    rec = _synthetic_record("baseline", 2, 64, 96, 0, 2011, frames="waves")
+    g = torch.Generator().manual_seed(2011)
+    smooth = lambda h, w: torch.sigmoid(torch.nn.functional.avg_pool2d(torch.randn(2, 1, h + 2, w + 2, generator=g), 3, 1))
+    rec["leaves"][("disp", 0, 0)] = smooth(64, 96)          # factor 1
+    rec["leaves"][("disp", 0, 3)] = smooth(2, 3)            # factor 32
+    _check(rec, "baseline-fac1-fac32")

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(s2::NT, S <= 2 ? 3 : 2) photo_score2_kernel(co
     __half* s_nz = reinterpret_cast<__half*>(s_stat + 3 * kPR * NT);      // [2][kPP][NT] stashed normals (S <= 2)
     __shared__ uint64_t s_bar;
     __shared__ float s_part[2 * TDL_MAX_SCALES][NT / 32];
+    __shared__ float s_pyr[NT / 32][2][3];                  // pyramid: per warp (8 tile rows) and column half, per channel
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int k16 = tid & 15, rg = tid >> 4;                // patch column pair / row group
@@ -143,35 +144,65 @@ __global__ void __launch_bounds__(s2::NT, S <= 2 ? 3 : 2) photo_score2_kernel(co
     reflect_fix2(s_tgt, 1 + S);
     __syncthreads();
 
-    // ---- area-downsampled target pyramid (F.interpolate(mode='area'), net.py:259) and disparity sums
+    // ---- the thread's patch: columns 2*k16, 2*k16+1, rows 4*rg .. 4*rg+3 of the tile
+    const int pc0 = kPC * k16, pr0 = kPR * rg;
+    const int poff = pr0 * BW + pc0;                        // (patch row 0 - 1, patch column 0) inside a staged plane
+
+    // ---- area-downsampled target pyramid (F.interpolate(mode='area'), net.py:259) and disparity sums, as a butterfly over
+    //      the patches: a thread adds its own 2x2 blocks, lanes exchange partial sums with shuffles (k16 is lane & 15, the
+    //      row group the lane's bit 4) and only the 16- and 32-pixel cells cross warps through 24 floats of shared
+    //      memory -- ~80 instructions per thread where the per-cell loops (runtime divisors, serial fac*fac sums, a handful
+    //      of busy threads on the coarse scales) took ~1900: 12 % of this kernel's instructions and of its stall samples
     float dsum[TDL_MAX_SCALES], lsum[TDL_MAX_SCALES];
 #pragma unroll
     for (int s = 0; s < TDL_MAX_SCALES; ++s) dsum[s] = lsum[s] = 0.f;
+    {
+        float lv2[3][2], lv4[3], lv8[3];
 #pragma unroll
-    for (int s = 0; s < TDL_MAX_SCALES; ++s) {
-        if (s < p.nscales) {
-            const int fac = p.fac[s], cells = TW / fac, h = p.dh[s], w = p.dw[s];
-            const int cj0 = ty0 / fac, ci0 = tx0 / fac;
-            const float inv = 1.f / (float)(fac * fac);
-            for (int i = tid; i < cells * cells * 3; i += NT) {
-                const int ch = i / (cells * cells), rem = i - ch * cells * cells;
-                const int cj = rem / cells, ci = rem - cj * cells;
-                if (cj0 + cj < h && ci0 + ci < w) {
-                    const float* base = s_tgt + ch * BPLANE + (1 + cj * fac) * BW + ci * fac;
-                    float acc = 0.f;
-                    for (int dy = 0; dy < fac; ++dy)
-                        for (int dx = 0; dx < fac; ++dx) acc += base[dy * BW + dx];
-                    const size_t o = (((size_t)b * 3 + ch) * h + cj0 + cj) * w + ci0 + ci;
-                    p.J[s][o] = acc * inv;
-                    if (ch == 0) dsum[s] += __ldg(p.disp[s] + ((size_t)b * h + cj0 + cj) * w + ci0 + ci);
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* t = s_tgt + ch * BPLANE + poff + BW;          // patch row 0
+            float2 v[kPR];
+#pragma unroll
+            for (int r = 0; r < kPR; ++r) v[r] = *reinterpret_cast<const float2*>(t + r * BW);
+            lv2[ch][0] = (v[0].x + v[0].y) + (v[1].x + v[1].y);
+            lv2[ch][1] = (v[2].x + v[2].y) + (v[3].x + v[3].y);
+            float a = lv2[ch][0] + lv2[ch][1];
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            lv4[ch] = a;                                                // 4 x 4 pixels
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 16);
+            lv8[ch] = a;                                                // 8 x 8
+            a += __shfl_xor_sync(0xffffffffu, a, 4);                    // 16 columns x the warp's 8 rows
+            if ((lane & 23) == 0) s_pyr[wrp][lane >> 3][ch] = a;        // lanes 0 and 8: column halves 0 and 1
+        }
+#pragma unroll
+        for (int s = 0; s < TDL_MAX_SCALES; ++s) {
+            if (s < p.nscales) {
+                const int fac = p.fac[s], h = p.dh[s], w = p.dw[s];
+                if (fac > 8) continue;                                  // the 16- / 32-pixel cells follow the next barrier
+                const bool owner = fac <= 2 || (fac == 4 ? (k16 & 1) == 0 : ((k16 & 3) == 0 && (rg & 1) == 0));
+                const int ncell = fac == 1 ? kPP : (fac == 2 ? 2 : 1);
+                const float inv = 1.f / (float)(fac * fac);
+#pragma unroll
+                for (int c = 0; c < kPP; ++c) {
+                    if (c < ncell && owner) {
+                        // cell c of the patch at this scale: fac 1: pixel c; fac 2: row pair c; fac 4 / 8: the one cell
+                        const int cj = (ty0 + pr0 + (fac == 1 ? c / kPC : (fac == 2 ? 2 * c : 0))) / fac;
+                        const int ci = (tx0 + pc0 + (fac == 1 ? c % kPC : 0)) / fac;
+                        if (cj < h && ci < w) {
+#pragma unroll
+                            for (int ch = 0; ch < 3; ++ch) {
+                                const float v = fac == 1 ? s_tgt[ch * BPLANE + poff + BW + (c / kPC) * BW + c % kPC]
+                                                         : (fac == 2 ? lv2[ch][c & 1] : (fac == 4 ? lv4[ch] : lv8[ch]));
+                                p.J[s][(((size_t)b * 3 + ch) * h + cj) * w + ci] = v * inv;
+                            }
+                            dsum[s] += __ldg(p.disp[s] + ((size_t)b * h + cj) * w + ci);
+                        }
+                    }
                 }
             }
         }
     }
-
-    // ---- the thread's patch: columns 2*k16, 2*k16+1, rows 4*rg .. 4*rg+3 of the tile
-    const int pc0 = kPC * k16, pr0 = kPR * rg;
-    const int poff = pr0 * BW + pc0;                        // (patch row 0 - 1, patch column 0) inside a staged plane
 
     float4* my_stat = s_stat + tid;
 #pragma unroll
@@ -236,6 +267,27 @@ __global__ void __launch_bounds__(s2::NT, S <= 2 ? 3 : 2) photo_score2_kernel(co
     float rho_id[S][kPP];
     if (p.automask) score_frames(s_img, rho_id);
     __syncthreads();                                        // every thread is done with the source tiles
+
+    // ---- the pyramid's 16- and 32-pixel cells from the per-warp partial sums (written before the barrier above)
+#pragma unroll
+    for (int s = 0; s < TDL_MAX_SCALES; ++s) {
+        if (s < p.nscales && p.fac[s] > 8) {
+            const int fac = p.fac[s], h = p.dh[s], w = p.dw[s];
+            const int cells = TW / fac;                              // 2 or 1 per tile side
+            if (tid < cells * cells * 3) {
+                const int ch = tid % 3, cell = tid / 3, cy = cell / cells, cx = cell - cy * cells;
+                float v;
+                if (fac == 16) v = s_pyr[2 * cy][cx][ch] + s_pyr[2 * cy + 1][cx][ch];
+                else v = ((s_pyr[0][0][ch] + s_pyr[0][1][ch]) + (s_pyr[1][0][ch] + s_pyr[1][1][ch])) +
+                         ((s_pyr[2][0][ch] + s_pyr[2][1][ch]) + (s_pyr[3][0][ch] + s_pyr[3][1][ch]));
+                const int cj = ty0 / fac + cy, ci = tx0 / fac + cx;
+                if (cj < h && ci < w) {
+                    p.J[s][(((size_t)b * 3 + ch) * h + cj) * w + ci] = v * (1.f / (float)(fac * fac));
+                    if (ch == 0) dsum[s] += __ldg(p.disp[s] + ((size_t)b * h + cj) * w + ci);
+                }
+            }
+        }
+    }
 
     const int gx0 = tx0 + pc0, gy0 = ty0 + pr0;
     for (int s = 0; s < p.nscales; ++s) {
