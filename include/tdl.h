@@ -269,9 +269,10 @@ int tdl_abi_version(void);
 const char* tdl_strerror(int code);
 /* Process-wide switches for tests and kernel experiments (the defaults are the product path).  They are
  * initialised once from the environment (TDL_NO_TMA, TDL_FUSED_FWD, TDL_PHOTO_SPARSE_MAX, TDL_FEAT_ATOMIC,
- * TDL_FEAT_CHUNK, TDL_PHOTO_V1, TDL_PHOTO_LIST_MAX) and afterwards only change through this call -- the entry points
+ * TDL_FEAT_CHUNK, TDL_PHOTO_V1, TDL_PHOTO_LIST_MAX, TDL_FEAT_NO_BULK) and afterwards only change through this call -- the entry points
  * never call getenv().
  * Names: "no_tma", "fused_fwd", "photo_sparse_max", "feat_atomic", "feat_chunk", "photo_v1" (round-1 scoring kernel),
+ * "feat_no_bulk" (channel-last feature forward with per-lane cp.async instead of TMA bulk copies),
  * "photo_list_max" (backward: (image, scale) pairs with at most this many selected windows run from the work list the
  * scoring kernel emits, default and maximum 4096; -1 = always the tile kernel). */
 int tdl_set_option(const char* name, int value);

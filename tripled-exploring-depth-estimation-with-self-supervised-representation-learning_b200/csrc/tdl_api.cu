@@ -19,10 +19,10 @@ namespace {
 
 // ---- process-wide tuning / test switches.  Read from the environment ONCE (first use) and afterwards only changed through
 // tdl_set_option(): the entry points below are on the training step's host path and must not call getenv().
-enum Opt { kOptNoTma = 0, kOptFusedFwd, kOptSparseMax, kOptFeatAtomic, kOptFeatChunk, kOptPhotoV1, kOptListMax, kOptCount };
-const char* const kOptNames[kOptCount] = {"no_tma", "fused_fwd", "photo_sparse_max", "feat_atomic", "feat_chunk", "photo_v1", "photo_list_max"};
-const char* const kOptEnv[kOptCount] = {"TDL_NO_TMA", "TDL_FUSED_FWD", "TDL_PHOTO_SPARSE_MAX", "TDL_FEAT_ATOMIC", "TDL_FEAT_CHUNK", "TDL_PHOTO_V1", "TDL_PHOTO_LIST_MAX"};
-const int kOptDefault[kOptCount] = {0, 0, 128, 0, 0, 0, kListCap};
+enum Opt { kOptNoTma = 0, kOptFusedFwd, kOptSparseMax, kOptFeatAtomic, kOptFeatChunk, kOptPhotoV1, kOptListMax, kOptFeatNoBulk, kOptCount };
+const char* const kOptNames[kOptCount] = {"no_tma", "fused_fwd", "photo_sparse_max", "feat_atomic", "feat_chunk", "photo_v1", "photo_list_max", "feat_no_bulk"};
+const char* const kOptEnv[kOptCount] = {"TDL_NO_TMA", "TDL_FUSED_FWD", "TDL_PHOTO_SPARSE_MAX", "TDL_FEAT_ATOMIC", "TDL_FEAT_CHUNK", "TDL_PHOTO_V1", "TDL_PHOTO_LIST_MAX", "TDL_FEAT_NO_BULK"};
+const int kOptDefault[kOptCount] = {0, 0, 128, 0, 0, 0, kListCap, 0};
 std::atomic<int> g_opt[kOptCount];
 std::once_flag g_opt_once;
 
@@ -442,6 +442,7 @@ static int check_feat(const tdl_feat_args* a, bool bwd, FeatDev* d) {
         return TDL_ERR_SHAPE;
     d->layout = a->layout;
     d->dtype = a->dtype;
+    d->bulk = !opt(kOptFeatNoBulk);
     d->tgt = static_cast<const float*>(a->tgt); d->disp = a->disp; d->P = a->P; d->invK = a->invK;
     int n_dsrc = 0;
     for (int f = 0; f < a->S; ++f) {

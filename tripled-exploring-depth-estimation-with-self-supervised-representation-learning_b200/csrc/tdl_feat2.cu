@@ -16,6 +16,7 @@
 
 #include "tdl_common.cuh"
 #include "tdl_internal.h"
+#include "tdl_tma.cuh"
 
 #include <cuda_bf16.h>
 
@@ -225,6 +226,205 @@ __global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_kernel(const FeatDev p) 
             advance(q, ck);
             if (q >= PIX) break;
             step(std::integral_constant<int, 2>{}, q, ck);
+            advance(q, ck);
+        }
+    }
+    __syncwarp();
+    // ---- lane = pixel again: minimum over the source frames
+    float best = 0.f;
+    {
+        const int pix = pix0 + lane;
+        if (pix < hw) {
+            const float fc = (float)C;
+            int arg = 0;
+            best = __fdiv_rn(s_res[wq][lane][0], fc);
+#pragma unroll
+            for (int f = 1; f < S; ++f) {
+                const float v = __fdiv_rn(s_res[wq][lane][f], fc);
+                if (v < best) {
+                    best = v;
+                    arg = f;
+                }
+            }
+            p.argmin[(size_t)b * hw + pix] = (unsigned char)arg;
+            if (p.min_index) p.min_index[(size_t)b * hw + pix] = arg;
+        }
+    }
+    best = block_sum(best, s_red);
+    if (tid == 0) atomicAdd(p.acc + b, (double)best);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Forward with TMA BULK COPIES (cp.async.bulk, SASS UBLKCP) instead of per-lane cp.async: one elected lane requests whole
+// rows -- the target row of a pixel (C values), and per source frame the north and the south tap PAIR as one 2-row copy
+// each when the east column is inside (a tap pair is contiguous in channel-last memory) -- straight into the warp's ring
+// in shared memory; completion is counted in bytes on one mbarrier per ring stage.  The rows no longer pass through the
+// LSU / L1 as 32 x 16-byte requests (L1/TEX was 82 % busy in the cp.async kernel), the ring needs two stages instead of
+// three (37 KB per CTA -> 6 CTAs / 24 warps per SM instead of 4 / 16), and the issue cost drops from 18 warp-wide copy
+// instructions per step to 10 single-lane ones.  profiles/microbench/rowgather.cu isolates the access pattern: 80 us
+// (cp.async, 3 stages) -> 57 us (bulk, 2 stages; deeper rings are SLOWER: 66 / 80 / 100 us at 3 / 4 / 6 stages, occupancy
+// matters more than depth).  Used for C == 64 k (64-channel chunks) and C < 64; other widths keep the cp.async kernel.
+TDL_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int S, typename T>
+__global__ void __launch_bounds__(f2::NT) feat_fwd_nhwc_bulk_kernel(const FeatDev p) {
+    using namespace f2;
+    __shared__ float s_cam[TDL_MAX_SRC * 12 + 9];
+    __shared__ Tap s_tap[NT / 32][PIX][S];
+    __shared__ float s_res[NT / 32][PIX][S];
+    __shared__ float s_red[32];
+    constexpr int kStages = 2;
+    __shared__ uint64_t s_bar[NT / 32][kStages];
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5, half = lane >> 4, l16 = lane & 15;
+    const int b = blockIdx.y;
+    const int h = p.h, w = p.w, C = p.C;
+    const int hw = h * w;
+    const unsigned uC = (unsigned)C;
+    if (tid < S * 12) s_cam[tid] = __ldg(p.P + (size_t)b * S * 12 + tid);
+    if (tid >= 64 && tid < 64 + 9) s_cam[TDL_MAX_SRC * 12 + tid - 64] = __ldg(p.invK + (size_t)b * 9 + tid - 64);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kStages; ++k) mbar_init(&s_bar[wq][k], 1);
+    }
+    __syncthreads();
+    const int pix0 = (blockIdx.x * (NT / 32) + wq) * PIX;
+    // ---- phase 1: lane = pixel
+    {
+        const int pix = min(pix0 + lane, hw - 1);
+        const int y = pix / w, x = pix - y * w;
+        const DepthParams dp{p.min_disp, p.range};
+        const UpTap ut = up_tap(y, x, p.sy, p.sx, p.dh, p.dw);
+        const Geo g = backproject(up_value(p.disp + (size_t)b * p.dh * p.dw, p.dw, ut), dp, s_cam + TDL_MAX_SRC * 12, x, y);
+        const ProjConst pc = make_proj_const(h, w, p.align_corners);
+#pragma unroll
+        for (int f = 0; f < S; ++f) {
+            const Proj pr = project<false>(g, s_cam + f * 12, pc);
+            const Bilin bt = bilin_taps(pr.ix, pr.iy, h, w);
+            s_tap[wq][lane][f] = Tap{(bt.y0 * w + bt.x0) | (bt.vx ? (1 << 30) : 0) | (bt.vy ? (1 << 29) : 0), bt.nw, bt.ne, bt.sw, bt.se};
+        }
+    }
+    __syncwarp();
+    // ---- phase 2: two pixels per step, one half-warp each; lane l of a half owns channels 4l .. 4l+3 of the chunk
+    const T* __restrict__ tgt = tdl::opaque(reinterpret_cast<const T*>(p.tgt) + (size_t)b * hw * C);
+    const T* __restrict__ srcb[S];
+    T* __restrict__ wrpb[S];
+#pragma unroll
+    for (int f = 0; f < S; ++f) {
+        srcb[f] = tdl::opaque(reinterpret_cast<const T*>(p.src[f]) + (size_t)b * hw * C);
+        wrpb[f] = p.warped[f] ? tdl::opaque(reinterpret_cast<T*>(p.warped[f]) + (size_t)b * hw * C) : nullptr;
+    }
+    constexpr int kRows = 1 + 4 * S;                        // rows per pixel: target + 4 taps per frame
+    constexpr int kRowStride = 64 * (int)sizeof(T);         // bytes between the rows of the ring (one 64-channel chunk)
+    constexpr int kLaneBytes = 4 * (int)sizeof(T);
+    extern __shared__ __align__(128) unsigned char s_ring_raw[];
+    // ring[warp][stage][pixel of the step][row][64 channels]
+    unsigned char* ring = s_ring_raw + (size_t)wq * kStages * 2 * kRows * kRowStride;
+    const int nchunk = (C + 63) / 64;
+    const unsigned rowB = (unsigned)min(C, 64) * (unsigned)sizeof(T);     // bytes of one row copy (a multiple of 16)
+    const bool pairs = C == 64;                             // a tap pair (west, east) is one contiguous 2-row copy
+    auto issue = [&](int q, int ck, int stage) {
+        __syncwarp();                                       // every lane has read the stage that is refilled
+        if (lane == 0) {
+            uint64_t* bar = &s_bar[wq][stage];
+            mbar_arrive_expect_tx(bar, 2u * kRows * rowB);
+            const unsigned cofs = 64u * (unsigned)ck;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int pl = q + hh;
+                const int pix = min(pix0 + pl, hw - 1);
+                unsigned char* d = ring + (size_t)((stage * 2 + hh) * kRows) * kRowStride;
+                bulk_g2s(d, tgt + ((unsigned)pix * uC + cofs), rowB, bar);
+#pragma unroll
+                for (int f = 0; f < S; ++f) {
+                    const int o00 = s_tap[wq][pl][f].o00;
+                    const int o = o00 & 0x1fffffff;
+                    const unsigned ex = ((o00 >> 30) & 1) ? uC : 0u, ey = ((o00 >> 29) & 1) ? (unsigned)w * uC : 0u;
+                    // a clamped tap has weight exactly 0: its slot receives the clamped row (finite values), like ATen's
+                    // skipped tap adds nothing
+                    const T* sb = srcb[f] + ((unsigned)o * uC + cofs);
+                    unsigned char* r = d + (size_t)(1 + 4 * f) * kRowStride;
+                    if (pairs && ex) {
+                        bulk_g2s(r, sb, 2 * rowB, bar);
+                        bulk_g2s(r + 2 * kRowStride, sb + ey, 2 * rowB, bar);
+                    } else {
+                        bulk_g2s(r, sb, rowB, bar);
+                        bulk_g2s(r + kRowStride, sb + ex, rowB, bar);
+                        bulk_g2s(r + 2 * kRowStride, sb + ey, rowB, bar);
+                        bulk_g2s(r + 3 * kRowStride, sb + (ey + ex), rowB, bar);
+                    }
+                }
+            }
+        }
+    };
+    auto rd = [&](int stage, int row) -> float4 {
+        const unsigned char* q = ring + (size_t)((stage * 2 + half) * kRows + row) * kRowStride + l16 * kLaneBytes;
+        if (sizeof(T) == 4) return *reinterpret_cast<const float4*>(q);
+        const uint2 u = *reinterpret_cast<const uint2*>(q);
+        return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                           __uint_as_float(u.y & 0xffff0000u));
+    };
+    float acc[S];
+#pragma unroll
+    for (int f = 0; f < S; ++f) acc[f] = 0.f;
+    const int cl = 4 * l16;
+    int iq = 0, ick = 0;                                     // (pixel pair, chunk) of the next step to request
+    auto advance = [&](int& q, int& ck) {
+        if (++ck == nchunk) {
+            ck = 0;
+            q += 2;
+        }
+    };
+    issue(iq, ick, 0);
+    advance(iq, ick);
+    uint32_t par[kStages] = {0u, 0u};
+    auto step = [&](auto stage_c, int q, int ck) {
+        constexpr int stage = decltype(stage_c)::value;
+        const int pl = q + half;
+        const int pix = pix0 + pl;
+        // request the next step into the stage consumed in the previous step, then wait for this step's bytes
+        if (iq < PIX) issue(iq, ick, stage ^ 1);
+        advance(iq, ick);
+        mbar_wait(&s_bar[wq][stage], par[stage]);
+        par[stage] ^= 1u;
+        const int c = cl + 64 * ck;
+        if (pix < hw && c < C) {
+            const float4 t = rd(stage, 0);
+#pragma unroll
+            for (int f = 0; f < S; ++f) {
+                const Tap tp = s_tap[wq][pl][f];
+                const float4 a = rd(stage, 1 + 4 * f), bq = rd(stage, 2 + 4 * f), cq = rd(stage, 3 + 4 * f), d = rd(stage, 4 + 4 * f);
+                float4 v;
+                v.x = a.x * tp.nw + bq.x * tp.ne + cq.x * tp.sw + d.x * tp.se;
+                v.y = a.y * tp.nw + bq.y * tp.ne + cq.y * tp.sw + d.y * tp.se;
+                v.z = a.z * tp.nw + bq.z * tp.ne + cq.z * tp.sw + d.z * tp.se;
+                v.w = a.w * tp.nw + bq.w * tp.ne + cq.w * tp.sw + d.w * tp.se;
+                if (wrpb[f]) st4(wrpb[f] + ((unsigned)pix * uC + (unsigned)c), v);
+                const float e0 = v.x - t.x, e1 = v.y - t.y, e2 = v.z - t.z, e3 = v.w - t.w;      // robust_l1(tgt_f, src_f)
+                const float t0 = fmaf(e0, e0, kL1Eps2), t1 = fmaf(e1, e1, kL1Eps2), t2 = fmaf(e2, e2, kL1Eps2), t3 = fmaf(e3, e3, kL1Eps2);
+                acc[f] += (t0 * rsqrt_approx(t0) + t1 * rsqrt_approx(t1)) + (t2 * rsqrt_approx(t2) + t3 * rsqrt_approx(t3));
+            }
+        }
+        if (ck == nchunk - 1) {                              // all chunks of this pixel pair done: reduce over the 16 lanes
+#pragma unroll
+            for (int f = 0; f < S; ++f) {
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], o);
+                if (l16 == 0) s_res[wq][pl][f] = acc[f];
+                acc[f] = 0.f;
+            }
+        }
+    };
+    {
+        int q = 0, ck = 0;
+        while (q < PIX) {
+            step(std::integral_constant<int, 0>{}, q, ck);
+            advance(q, ck);
+            if (q >= PIX) break;
+            step(std::integral_constant<int, 1>{}, q, ck);
             advance(q, ck);
         }
     }
@@ -618,6 +818,14 @@ static cudaError_t fwd_st(const FeatDev& p, cudaStream_t st) {
     static SmemOptIn opt_in;
     if (cudaError_t e = opt_in(feat_fwd_nhwc_kernel<S, T>, smem)) return e;
     dim3 grid((unsigned)((p.h * p.w + NT - 1) / NT), p.B);
+    if (p.bulk && (p.C < 64 || p.C % 64 == 0)) {
+        // bulk-copy ring: 2 stages x 2 pixels x (1 + 4S) rows x 64 channels per warp
+        const size_t smem_b = (size_t)(NT / 32) * 2 * 2 * (1 + 4 * S) * 64 * sizeof(T);
+        static SmemOptIn opt_in_b;
+        if (cudaError_t e = opt_in_b(feat_fwd_nhwc_bulk_kernel<S, T>, smem_b)) return e;
+        feat_fwd_nhwc_bulk_kernel<S, T><<<grid, NT, smem_b, st>>>(p);
+        return cudaGetLastError();
+    }
     feat_fwd_nhwc_kernel<S, T><<<grid, NT, smem, st>>>(p);
     return cudaGetLastError();
 }

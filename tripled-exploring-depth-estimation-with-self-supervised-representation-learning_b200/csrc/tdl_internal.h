@@ -99,6 +99,7 @@ struct SmoothDev {
 // ---- feature-metric ----------------------------------------------------------------
 struct FeatDev {
     int B, C, h, w, S;
+    int bulk;                    // NHWC forward: rows travel by TMA bulk copies (option feat_no_bulk = 0)
     int layout, dtype;           // TDL_LAYOUT_* / TDL_DTYPE_* of tgt, src, warped, d_tgt, d_src (bf16 pointers are carried as float*)
     int Bnorm;                   // batch size of the mean (== B except for the batch chunks of the bucketed backward)
     int dh, dw;
