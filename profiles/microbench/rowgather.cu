@@ -144,6 +144,82 @@ float run(const float* t, const float* a, const float* b, float* o) {
     return ms / 20 * 1e3f;
 }
 
+// MODE 2: bulk copies, ONE pixel per step (the whole warp reads it, 8 bytes per lane): half the stage size, twice the CTAs
+template <int STAGES>
+__global__ void __launch_bounds__(NT) gather1(const float* __restrict__ tgt, const float* __restrict__ s0, const float* __restrict__ s1,
+                                              float* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char raw[];
+    __shared__ uint64_t bars[NT / 32][STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+    const int b = blockIdx.y, pix0 = (blockIdx.x * (NT / 32) + wq) * PIX;
+    const size_t img = (size_t)b * H * W * C;
+    const float* src[2] = {s0 + img, s1 + img};
+    float* ring = reinterpret_cast<float*>(raw) + (size_t)wq * STAGES * ROWS * C;
+    if (lane == 0)
+        for (int k = 0; k < STAGES; ++k) mbar_init(&bars[wq][k], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    auto issue = [&](int q, int stage) {
+        float* d = ring + (size_t)stage * ROWS * C;
+        __syncwarp();
+        if (lane == 0) {
+            mbar_expect(&bars[wq][stage], ROWS * C * 4);
+            const int pix = pix0 + q, y = pix / W, x = pix - y * W;
+            bulk(d, tgt + img + (size_t)pix * C, C * 4, &bars[wq][stage]);
+#pragma unroll
+            for (int f = 0; f < S; ++f) {
+                const int o = tap_of(y, x, f);
+                const float* sb = src[f] + (size_t)o * C;
+                bulk(d + (1 + 4 * f) * C, sb, 2 * C * 4, &bars[wq][stage]);
+                bulk(d + (3 + 4 * f) * C, sb + (size_t)W * C, 2 * C * 4, &bars[wq][stage]);
+            }
+        }
+    };
+    float acc = 0.f;
+    int iq = 0;
+    for (int k = 0; k < STAGES - 1; ++k, ++iq) issue(iq, k);
+    uint32_t par[STAGES] = {};
+    int stage = 0;
+    for (int q = 0; q < PIX; ++q) {
+        if (iq < PIX) issue(iq, (stage + STAGES - 1) % STAGES);
+        ++iq;
+#pragma unroll
+        for (int k = 0; k < STAGES; ++k)
+            if (k == stage) {
+                mbar_wait(&bars[wq][k], par[k]);
+                par[k] ^= 1;
+            }
+        const float* st = ring + (size_t)stage * ROWS * C + 2 * lane;
+        const float2 t = *reinterpret_cast<const float2*>(st);
+#pragma unroll
+        for (int r = 1; r < ROWS; ++r) {
+            const float2 v = *reinterpret_cast<const float2*>(st + r * C);
+            acc += (v.x - t.x) + (v.y - t.y);
+        }
+        stage = stage + 1 == STAGES ? 0 : stage + 1;
+    }
+    out[((size_t)b * gridDim.x + blockIdx.x) * NT + tid] = acc;
+}
+
+template <int STAGES>
+float run1(const float* t, const float* a, const float* b, float* o) {
+    const size_t smem = (size_t)(NT / 32) * STAGES * ROWS * C * 4;
+    cudaFuncSetAttribute(gather1<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(H * W / ((NT / 32) * PIX), B);
+    gather1<STAGES><<<grid, NT, smem>>>(t, a, b, o);
+    cudaDeviceSynchronize();
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    for (int i = 0; i < 20; ++i) gather1<STAGES><<<grid, NT, smem>>>(t, a, b, o);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    return ms / 20 * 1e3f;
+}
+
 int main() {
     const size_t n = (size_t)B * H * W * C;
     float *t, *a, *b, *o;
@@ -161,6 +237,8 @@ int main() {
                bytes / us1 * 1e-3);
         const float u2 = run<1, 2>(t, a, b, o), u4 = run<1, 4>(t, a, b, o), u6 = run<1, 6>(t, a, b, o), l4 = run<0, 4>(t, a, b, o);
         printf("bulk ring 2 / 4 / 6 stages: %.1f / %.1f / %.1f us   LDGSTS 4 stages: %.1f us\n", u2, u4, u6, l4);
+        printf("bulk, one pixel per step, 2 / 3 / 4 stages: %.1f / %.1f / %.1f us   LDGSTS 2 stages: %.1f us\n", run1<2>(t, a, b, o),
+               run1<3>(t, a, b, o), run1<4>(t, a, b, o), run<0, 2>(t, a, b, o));
     }
     return 0;
 }
