@@ -27,7 +27,7 @@ REP=gpurun_out/${TAG}_full.ncu-rep
   echo; echo "## Speed-of-light section per kernel (\`ncu --page details\`)"; echo; echo '```'
   ncu -i $REP --page details 2>/dev/null | grep -E "^  [a-z_A-Z].*\(|L1/TEX Cache Throughput|Issue Slots Busy|DRAM Throughput|Duration  |L2 Cache Throughput|Mem Pipes Busy|Achieved Occupancy|Theoretical Occupancy|Registers Per Thread"
   echo '```'
-  for k in "photo_score2:photo_score2_kernelILi2E:tdl_photo2" "photo_bwd_kernel:photo_bwd_kernelILi2ELb1E:tdl_photo" "feat_fwd_nhwc:feat_fwd_nhwc_kernelILi2EfE:tdl_feat2"; do
+  for k in "photo_score2:photo_score2_kernelILi2E:tdl_photo2" "photo_bwd_kernel:photo_bwd_kernelILi2ELb1E:tdl_photo" "feat_fwd_nhwc:feat_fwd_nhwc_bulk_kernelILi2EfE:tdl_feat2"; do
     IFS=: read rx mang cub <<< "$k"
     echo; echo "## \`$rx\`: SASS opcode histogram (\`profiles/sass_opcount.py\`)"; echo; echo '```'
     python profiles/sass_opcount.py $REP $rx 2>/dev/null | head -14; echo '```'
@@ -43,7 +43,7 @@ import csv, json, subprocess, sys
 rep, tag = sys.argv[1], sys.argv[2]
 out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines())); hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
-names = {'photo_warp_kernel': 'photo_warp', 'photo_score2_kernel': 'photo_score', 'feat_fwd_nhwc_kernel': 'feat_fwd',
+names = {'photo_warp_kernel': 'photo_warp', 'photo_score2_kernel': 'photo_score', 'feat_fwd_nhwc_kernel': 'feat_fwd', 'feat_fwd_nhwc_bulk_kernel': 'feat_fwd',
          'feat_bwd_nhwc_kernel': 'feat_bwd', 'photo_bwd_kernel': 'photo_bwd', 'feat_gather_nhwc_kernel': 'feat_gather',
          'smooth_fwd_kernel': 'smooth_fwd', 'smooth_bwd_kernel': 'smooth_bwd'}
 def tob(col, r):

@@ -109,3 +109,22 @@ def test_bf16_storage_matches_fp32_on_rounded_inputs(B, C, h, w, S):
         # atomics (they dominate the norm of d_src on this fixture): opt-in storage mode, never the parity configuration
         tol = 1e-5 if name in ("d_disp", "dP") else (8e-3 if name == "d_tgt" else 1e-1)
         assert rel_l2(gb, ga) < tol, (name, rel_l2(gb, ga))
+
+
+@pytest.mark.parametrize("B,C,h,w,S,shift", [(2, 64, 96, 320, 2, 0.05), (1, 128, 48, 80, 2, 0.3), (1, 16, 50, 70, 3, 0.5)])
+def test_bulk_copy_rings_equal_the_cp_async_rings(B, C, h, w, S, shift):
+    """feat_fwd / feat_bwd move their rows by TMA bulk copies (default) or by per-lane cp.async (option feat_no_bulk): only
+    the data movement differs, so every per-pixel result is bit-identical; the atomically accumulated ones agree to rounding."""
+    args = _inputs(B, C, h, w, S, 4700 + C, shift)
+    loss_a, warped_a, idx_a, grads_a = _run(args, "nhwc")
+    with pkg()._lib.options(feat_no_bulk=1):
+        loss_b, warped_b, idx_b, grads_b = _run(args, "nhwc")
+    assert abs(loss_a - loss_b) <= 1e-7 * abs(loss_a) and torch.equal(idx_a, idx_b)   # (fp64 atomics of per-CTA sums)
+    for wa, wb in zip(warped_a, warped_b):
+        assert torch.equal(wa, wb)
+    names = ["d_tgt", "d_disp", "dP"] + [f"d_src{f}" for f in range(S)]
+    for name, ga, gb in zip(names, grads_a, grads_b):
+        if name == "d_tgt":
+            assert torch.equal(ga, gb), name
+        else:                                      # bucket slot order / atomics: same terms, another summation order
+            assert rel_l2(gb, ga) < 1e-5, (name, rel_l2(gb, ga))
