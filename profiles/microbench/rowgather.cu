@@ -30,14 +30,21 @@ __device__ __forceinline__ void bulk(void* dst, const void* src, uint32_t bytes,
 }
 
 // tap position of pixel (y, x) for frame f: a smooth displacement field, like a coherent flow
+#ifndef COHERENT
+#define COHERENT 0
+#endif
 __device__ __forceinline__ int tap_of(int y, int x, int f) {
     int ty = y + ((x * 7 + y * 3 + f * 11) % 5) - 2, tx = x + ((x * 5 + y * 13 + f * 7) % 9) - 4;
+    if (COHERENT) {                                        // a smooth flow: neighbouring pixels sample neighbouring positions
+        ty = y + 1 + f + ((y >> 3) & 1);
+        tx = x + 2 - 3 * f + ((x >> 4) & 1);
+    }
     ty = min(max(ty, 0), H - 2);
     tx = min(max(tx, 0), W - 2);
     return ty * W + tx;
 }
 
-template <int MODE, int STAGES>
+template <int MODE, int STAGES, bool MERGE = false, bool PAR = false>
 __global__ void __launch_bounds__(NT) gather(const float* __restrict__ tgt, const float* __restrict__ s0, const float* __restrict__ s1,
                                              float* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char raw[];
@@ -75,8 +82,31 @@ __global__ void __launch_bounds__(NT) gather(const float* __restrict__ tgt, cons
             asm volatile("cp.async.commit_group;" ::: "memory");
         } else {
             __syncwarp();                                   // every lane has read the stage that is refilled
-            if (lane == 0) {
-                mbar_expect(&bars[wq][stage], 2 * ROWS * C * 4);
+            if (PAR) {
+                // lanes 0 .. 2 * (1 + 2S) - 1 request one copy each: lane = pixel of the step x {target, (frame, north | south)}
+                if (lane == 0) mbar_expect(&bars[wq][stage], 2 * ROWS * C * 4);
+                __syncwarp();
+                constexpr int PER = 1 + 2 * S;
+                if (lane < 2 * PER) {
+                    const int hh = lane / PER, k = lane - hh * PER;
+                    const int pix = pix0 + q + hh, y = pix / W, x = pix - y * W;
+                    float* d = st + (size_t)hh * ROWS * C;
+                    if (k == 0) bulk(d, tgt + img + (size_t)pix * C, C * 4, &bars[wq][stage]);
+                    else {
+                        const int f = (k - 1) >> 1, south = (k - 1) & 1;
+                        const int o = tap_of(y, x, f);
+                        bulk(d + (1 + 4 * f + 2 * south) * C, src[f] + (size_t)o * C + (south ? (size_t)W * C : 0), 2 * C * 4, &bars[wq][stage]);
+                    }
+                }
+            } else if (lane == 0) {
+                uint32_t bytes = 2 * ROWS * C * 4;
+                if (MERGE) {
+                    const int pixa = pix0 + q, ya = pixa / W, xa = pixa - ya * W;
+#pragma unroll
+                    for (int f = 0; f < S; ++f)
+                        if (tap_of(ya, xa + 1, f) == tap_of(ya, xa, f) + 1) bytes -= 2 * C * 4;   // 2 x 3 rows instead of 4 x 2
+                }
+                mbar_expect(&bars[wq][stage], bytes);
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int pix = pix0 + q + hh, y = pix / W, x = pix - y * W;
@@ -86,6 +116,17 @@ __global__ void __launch_bounds__(NT) gather(const float* __restrict__ tgt, cons
                     for (int f = 0; f < S; ++f) {
                         const int o = tap_of(y, x, f);
                         const float* sb = src[f] + (size_t)o * C;
+                        if (MERGE) {
+                            // the two pixels of a step are neighbours: when their taps are too, one 3-row copy serves both
+                            const int oa = tap_of(y, x - hh, f), ob = tap_of(y, x - hh + 1, f);
+                            if (ob == oa + 1) {
+                                if (hh == 0) {
+                                    bulk(d + (1 + 4 * f) * C, sb, 3 * C * 4, &bars[wq][stage]);
+                                    bulk(d + (1 + 4 * f) * C + (size_t)ROWS * C, sb + (size_t)W * C, 3 * C * 4, &bars[wq][stage]);
+                                }
+                                continue;
+                            }
+                        }
                         bulk(d + (1 + 4 * f) * C, sb, 2 * C * 4, &bars[wq][stage]);                       // nw, ne
                         bulk(d + (3 + 4 * f) * C, sb + (size_t)W * C, 2 * C * 4, &bars[wq][stage]);       // sw, se
                     }
@@ -123,18 +164,18 @@ __global__ void __launch_bounds__(NT) gather(const float* __restrict__ tgt, cons
     out[((size_t)b * gridDim.x + blockIdx.x) * NT + tid] = acc;
 }
 
-template <int MODE, int STAGES>
+template <int MODE, int STAGES, bool MERGE = false, bool PAR = false>
 float run(const float* t, const float* a, const float* b, float* o) {
     const size_t smem = (size_t)(NT / 32) * STAGES * 2 * ROWS * C * 4;
-    cudaFuncSetAttribute(gather<MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gather<MODE, STAGES, MERGE, PAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(H * W / ((NT / 32) * PIX), B);
-    gather<MODE, STAGES><<<grid, NT, smem>>>(t, a, b, o);
+    gather<MODE, STAGES, MERGE, PAR><<<grid, NT, smem>>>(t, a, b, o);
     cudaDeviceSynchronize();
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    for (int i = 0; i < 20; ++i) gather<MODE, STAGES><<<grid, NT, smem>>>(t, a, b, o);
+    for (int i = 0; i < 20; ++i) gather<MODE, STAGES, MERGE, PAR><<<grid, NT, smem>>>(t, a, b, o);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
@@ -237,6 +278,8 @@ int main() {
                bytes / us1 * 1e-3);
         const float u2 = run<1, 2>(t, a, b, o), u4 = run<1, 4>(t, a, b, o), u6 = run<1, 6>(t, a, b, o), l4 = run<0, 4>(t, a, b, o);
         printf("bulk ring 2 / 4 / 6 stages: %.1f / %.1f / %.1f us   LDGSTS 4 stages: %.1f us\n", u2, u4, u6, l4);
+        printf("COHERENT=%d: bulk 2 stages unmerged %.1f us, merged triples %.1f us\n", COHERENT, run<1, 2>(t, a, b, o), run<1, 2, true>(t, a, b, o));
+        printf("bulk 2 / 3 stages, one copy per lane (10 lanes): %.1f / %.1f us\n", run<1, 2, false, true>(t, a, b, o), run<1, 3, false, true>(t, a, b, o));
         printf("bulk, one pixel per step, 2 / 3 / 4 stages: %.1f / %.1f / %.1f us   LDGSTS 2 stages: %.1f us\n", run1<2>(t, a, b, o),
                run1<3>(t, a, b, o), run1<4>(t, a, b, o), run<0, 2>(t, a, b, o));
     }
