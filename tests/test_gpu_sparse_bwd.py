@@ -81,7 +81,7 @@ def test_list_backward_agrees_with_tile_backward(frames, B, H, W, fids, expect):
     rec = _synthetic_record("baseline", B, H, W, 0, 5300 + H, frames=frames, frame_ids=fids)
     noise = reference_noise(spec_from_meta(rec["meta"]), rec["meta"])
     counts = [c for per in _selected_per_pair(rec, noise).values() for c in per]
-    cap = 4096
+    cap = pkg()._lib.get_option("photo_list_max")          # default = the list capacity (4096)
     if expect == "listed":
         assert 0 < max(counts) <= cap, counts
     elif expect == "tiles":
@@ -117,7 +117,7 @@ def test_list_backward_border_windows():
     list path."""
     rec = _synthetic_record("baseline", 1, 64, 96, 0, 5500, frames="smooth")
     noise = reference_noise(spec_from_meta(rec["meta"]), rec["meta"])
-    assert max(_selected_per_pair(rec, noise)[0]) <= 4096
+    assert max(_selected_per_pair(rec, noise)[0]) <= pkg()._lib.get_option("photo_list_max")
     _, outs, _ = run_cuda(rec, noise)
     sel = outs[("min_index", 0)] >= 2
     if not bool(sel[:, 0, :].any() or sel[:, -1, :].any() or sel[:, :, 0].any() or sel[:, :, -1].any()):

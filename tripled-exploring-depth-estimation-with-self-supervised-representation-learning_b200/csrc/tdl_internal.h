@@ -32,7 +32,8 @@ struct DepthParamsH {
 };
 
 // ---- photometric + smoothness, device-side view of tdl_photo_args -------------
-constexpr int kListCap = 4096;           // work-list entries per (image, scale)
+constexpr int kListCap = 4096;           // work-list entries per (image, scale); 8192 measured worse: the list kernel's time is set
+                                         // by its LONGEST list (74 CTAs per pair sweep it serially): 44 -> 85 us on the bench's smooth batch
 constexpr int kListMagic = 0x5C0DE2;     // written by photo_score2_kernel after the lists of a forward are complete
 
 struct PhotoDev {
