@@ -51,19 +51,20 @@ class GpuInputPipeline:
         holes (B,count,2) int32 or None."""
         F = len(self.frame_ids)
         g = generator
-        u = lambda: float(torch.rand((), generator=g))
-        jitter = torch.ones(B, F, 4, dtype=torch.float32)
-        order = torch.zeros(B, F, 4, dtype=torch.int32)
-        do_aug = torch.zeros(B, dtype=torch.uint8)
-        do_flip = torch.zeros(B, dtype=torch.uint8)
-        for b in range(B):
-            do_aug[b] = 1 if (self.is_train and u() > 0.5) else 0          # mono_dataset.py:140
-            do_flip[b] = 1 if (self.is_train and u() > 0.5) else 0         # mono_dataset.py:141
-            for f in range(F):                                             # a ColorJitter call per frame (:102)
-                order[b, f] = torch.randperm(4, generator=g).to(torch.int32)
-                for k, (lo, hi) in enumerate((self.brightness, self.contrast, self.saturation)):
-                    jitter[b, f, k] = float(torch.empty(1).uniform_(lo, hi, generator=g))
-                jitter[b, f, 3] = float(hue_shift_byte(float(torch.empty(1).uniform_(self.hue[0], self.hue[1], generator=g))))
+        # one vectorised draw per quantity (a few hundred numbers per batch): the same distributions as the per-item
+        # calls of the reference -- random.random() > 0.5 twice per item (mono_dataset.py:140-141), then per frame
+        # ColorJitter.get_params: a random permutation of the four operations and one uniform factor each
+        coin = torch.rand(B, 2, generator=g)
+        do_aug = ((coin[:, 0] > 0.5) & bool(self.is_train)).to(torch.uint8)
+        do_flip = ((coin[:, 1] > 0.5) & bool(self.is_train)).to(torch.uint8)
+        order = torch.rand(B, F, 4, generator=g).argsort(dim=-1).to(torch.int32)          # uniform over the 24 orders
+        u = torch.rand(B, F, 4, generator=g, dtype=torch.float64)
+        lo = torch.tensor([self.brightness[0], self.contrast[0], self.saturation[0], self.hue[0]], dtype=torch.float64)
+        hi = torch.tensor([self.brightness[1], self.contrast[1], self.saturation[1], self.hue[1]], dtype=torch.float64)
+        val = lo + (hi - lo) * u
+        jitter = val.to(torch.float32)
+        # the byte torchvision adds to the hue channel: uint8(int32(hue_factor * 255)), truncation toward zero then wrap
+        jitter[..., 3] = torch.remainder(torch.trunc(val[..., 3] * 255), 256).to(torch.float32)
         holes = None
         if self.erase_count > 0:
             eh, ew = self.erase_shape
